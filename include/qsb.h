@@ -1,0 +1,225 @@
+/* qsb.h -- C ABI of the B200-native cycle-tracking path for Quicksilver-class Monte Carlo transport.
+ *
+ * The reference (LLNL/Quicksilver) has no plugin/FFI interface; its de-facto boundary is
+ *   void CycleTrackingGuts(MonteCarlo*, int particle_index, ParticleVault* processing, ParticleVault* processed)
+ *   (src/CycleTracking.hh:8-14), selected by the ExecutionPolicy switch inside
+ *   cycleTracking(MonteCarlo*) (src/main.cc:138-307, src/cudaUtils.hh:10-25).
+ * This header is what a maintainer would bind in its place: plain pointers and sizes, no C++ or torch
+ * types, every call returns 0 or a negative qsb_status and never throws or aborts (the reference's own
+ * convention is "print and continue", src/qs_assert.hh:9-26; here the message is kept in
+ * qsb_last_error()).  INTEGRATION.md shows the binding.
+ *
+ * Three groups of entry points:
+ *   qsb_mc_*    host model: the reference's Parameters / initMC / cycleInit / cycleFinalize surface
+ *               (deck + CLI parsing, mesh + nuclear-data construction, source, population control,
+ *               balance bookkeeping).  Pure host code, usable without a GPU.
+ *   qsb_*       device context: one per GPU; uploads the flattened problem image, owns the SoA particle
+ *               vaults, runs the tracking kernels.  This is the hot path.  There is NO CPU fallback:
+ *               every call fails with QSB_ERR_CUDA when no sm_100 device is usable.
+ *   qsb_mc_cycle_tracking   the drop-in for the reference's cycleTracking(): host vault -> device,
+ *               track to exhaustion, census + tallies back to the host model.
+ */
+#ifndef QSB_H
+#define QSB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QSB_ABI_VERSION 1
+
+typedef enum qsb_status {
+    QSB_OK            =  0,
+    QSB_ERR_ARG       = -1,   /* bad argument / null pointer                      */
+    QSB_ERR_INPUT     = -2,   /* deck or command line could not be understood      */
+    QSB_ERR_CUDA      = -3,   /* CUDA runtime error or no usable device            */
+    QSB_ERR_CAPACITY  = -4,   /* a fixed-capacity vault or slab overflowed         */
+    QSB_ERR_STATE     = -5,   /* call made in the wrong phase of a cycle           */
+    QSB_ERR_INTERNAL  = -6
+} qsb_status;
+
+/* ---- particle record: byte-for-byte the reference's MC_Base_Particle (src/MC_Base_Particle.hh:75-92,
+ *      136 bytes: 12 f64, 2 u64, 6 i32) so host vaults can be handed over without conversion. ---- */
+typedef struct qsb_base_particle {
+    double   coordinate[3];
+    double   velocity[3];
+    double   kinetic_energy;
+    double   weight;
+    double   time_to_census;
+    double   age;
+    double   num_mean_free_paths;
+    double   num_segments;
+    uint64_t random_number_seed;
+    uint64_t identifier;
+    int32_t  last_event;        /* MC_Tally_Event (src/Tallies.hh:24-35)            */
+    int32_t  num_collisions;
+    int32_t  breed;
+    int32_t  species;           /* -1 = invalid slot                                 */
+    int32_t  domain;            /* rank-local domain index                           */
+    int32_t  cell;              /* domain-local cell index                           */
+} qsb_base_particle;
+
+/* balance counters in the order the reference reduces them (src/Tallies.cc:31-43) */
+enum { QSB_BAL_ABSORB = 0, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_END, QSB_BAL_FISSION,
+       QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_START, QSB_BAL_SOURCE, QSB_BAL_RR, QSB_BAL_SPLIT,
+       QSB_BAL_NUM_SEGMENTS, QSB_BAL_COUNT };
+
+/* facet adjacency events (src/MC_Facet_Adjacency.hh:9-20) */
+enum { QSB_ADJ_UNDEFINED = 0, QSB_ADJ_ESCAPE = 1, QSB_ADJ_REFLECT = 2, QSB_ADJ_TRANSIT_ON = 3, QSB_ADJ_TRANSIT_OFF = 4 };
+
+/* tally events (src/Tallies.hh:24-35) */
+enum { QSB_EV_COLLISION = 0, QSB_EV_FACET_TRANSIT = 1, QSB_EV_CENSUS = 2, QSB_EV_TRACKING_ERROR = 3,
+       QSB_EV_ESCAPE = 4, QSB_EV_REFLECTION = 5, QSB_EV_COMMUNICATION = 6 };
+
+/* reaction types (src/NuclearData.hh:33-39) */
+enum { QSB_REACT_UNDEFINED = 0, QSB_REACT_SCATTER = 1, QSB_REACT_ABSORPTION = 2, QSB_REACT_FISSION = 3 };
+
+/* ---- flattened, read-only problem image: what the tracking path reads.  All the rank's domains are
+ *      concatenated into one cell index space ("flat cell" = domain_cell_offset[domain] + cell).
+ *      Every value is bit-identical to what the reference computes for the same deck (pinned by
+ *      oracle/ref_dump.cc).  Pointers are borrowed from the qsb_mc that built them. ---- */
+typedef struct qsb_image {
+    int32_t  abi_version;
+    int32_t  n_domains;              /* domains held by this rank (src/initMC.cc:256-259)            */
+    int32_t  n_cells;                /* over all local domains                                        */
+    int32_t  n_groups;
+    int32_t  n_materials;
+    int32_t  n_isotopes;             /* over all materials                                            */
+    int32_t  max_reactions_per_material; /* max over materials of nIsotopes*nReactions                */
+    int32_t  my_rank, n_ranks;
+    int32_t  global_nx, global_ny, global_nz;
+    double   global_lx, global_ly, global_lz;
+    const int32_t*  domain_cell_offset;  /* [n_domains+1]                                             */
+    const int32_t*  domain_gid;          /* [n_domains] global domain id                              */
+    /* geometry, per flat cell */
+    const double*   planes;          /* [n_cells][24][4] A,B,C,D  (src/MC_Facet_Geometry.hh:18-39)     */
+    const double*   nodes;           /* [n_cells][14][3] the cell's own 14 points (src/GlobalFccGrid.cc:48-70) */
+    const int32_t*  cell_gid;        /* [n_cells] global cell id ix + nx*(iy + ny*iz)                 */
+    const int32_t*  cell_material;   /* [n_cells]                                                     */
+    const double*   cell_volume;     /* [n_cells]                                                     */
+    const uint64_t* cell_id;         /* [n_cells] seed base, gid << 32 (src/MC_Domain.cc:390)         */
+    /* adjacency, per flat cell and FACE (the 4 facets of a face share it: src/MC_Domain.cc:292-318) */
+    const uint8_t*  face_event;      /* [n_cells][6] QSB_ADJ_*                                        */
+    const int32_t*  face_adj_cell;   /* [n_cells][6] on-processor: flat cell; off-processor: cell index
+                                        local to the neighbour's domain; boundary: own flat cell      */
+    const int32_t*  face_adj_domain; /* [n_cells][6] neighbour's rank-local domain index              */
+    const int32_t*  face_nbr_rank;   /* [n_cells][6] owning rank for off-processor faces, else -1     */
+    /* nuclear data */
+    const double*   energies;        /* [n_groups+1] group edges (src/NuclearData.cc:105-119)         */
+    const int32_t*  mat_n_isotopes;  /* [n_materials]                                                 */
+    const int32_t*  mat_n_reactions; /* [n_materials] reactions per isotope                           */
+    const double*   mat_mass;        /* [n_materials]                                                 */
+    const double*   mat_nu_bar;      /* [n_materials] nuBar of the material's reactions               */
+    const uint8_t*  mat_react_type;  /* [n_materials][max_reactions_per_material] QSB_REACT_* by (iso,react) */
+    const double*   xs_total;        /* [n_materials][n_groups] = weightedMacroscopicCrossSection
+                                        (src/MacroscopicCrossSection.cc:59-80); identical for every
+                                        cell of a material because cellNumberDensity == 1
+                                        (src/MC_Domain.cc:387)                                        */
+    const double*   xs_react;        /* [n_materials][n_groups][max_reactions_per_material]
+                                        atomFraction*density*sigma in (iso,react) scan order
+                                        (src/CollisionEvent.cc:67-83)                                 */
+    const uint8_t*  mat_periodic;    /* [n_materials] 1 if every isotope of the material carries the
+                                        same reaction table (always true for reference decks)        */
+} qsb_image;
+
+/* ======================================================================================================
+ * Host model (qsb_mc_*)
+ * ==================================================================================================== */
+typedef struct qsb_mc qsb_mc;
+
+/* sum-reduction over ranks used by cycleInit/cycleFinalize, the stand-in for mpiAllreduce
+ * (src/utilsMpi.hh:24-50).  dtype: 0 = f64, 1 = u64.  In place.  NULL (default) = single rank. */
+typedef void (*qsb_allreduce_fn)(void* user, void* buf, int32_t count, int32_t dtype);
+
+/* Parse argv exactly like the reference's getParameters (CLI first, deck overrides: src/Parameters.cc:80-95)
+ * and build the rank's MonteCarlo model (src/initMC.cc:53-74).  rank/n_ranks replace MPI_Comm_rank/size. */
+int  qsb_mc_create(int argc, const char* const* argv, int rank, int n_ranks, qsb_mc** out);
+int  qsb_mc_destroy(qsb_mc* mc);
+int  qsb_mc_set_allreduce(qsb_mc* mc, qsb_allreduce_fn fn, void* user);
+/* echo of the parameters in deck syntax ("output is a valid input", src/Parameters.cc:97-215). */
+int  qsb_mc_print_parameters(qsb_mc* mc, char* buf, uint64_t cap, uint64_t* needed);
+int  qsb_mc_get_image(qsb_mc* mc, qsb_image* out);
+int  qsb_mc_get_int(qsb_mc* mc, const char* key, int64_t* out);       /* nSteps, nParticles, nx, xDom, ... */
+int  qsb_mc_get_double(qsb_mc* mc, const char* key, double* out);     /* dt, lx, eMin, source_particle_weight ... */
+
+/* cycleInit (src/main.cc:96-121): swap census -> processing, source, population control, roulette. */
+int  qsb_mc_cycle_init(qsb_mc* mc);
+/* processing vault (tracking input) as one contiguous AoS; valid until the next qsb_mc_* call. */
+int  qsb_mc_processing(qsb_mc* mc, const qsb_base_particle** aos, uint64_t* n);
+/* hand the tracker's result back: census particles become the processed vault, counters are added to
+ * this cycle's balance task (only the tracking counters are read: absorb, census, escape, collision,
+ * fission, produce, scatter, num_segments). */
+int  qsb_mc_set_tracking_result(qsb_mc* mc, const qsb_base_particle* census, uint64_t n_census,
+                                const uint64_t balance[QSB_BAL_COUNT], double scalar_flux_sum);
+/* cycleFinalize (src/main.cc:310-324, src/Tallies.cc:25-98): reduce, accumulate, roll _start.
+ * row[0..12] = this cycle's global balance in QSB_BAL_* order, *flux = global scalar-flux sum. */
+int  qsb_mc_cycle_finalize(qsb_mc* mc, uint64_t row[QSB_BAL_COUNT], double* flux);
+int  qsb_mc_cumulative_balance(qsb_mc* mc, uint64_t out[QSB_BAL_COUNT]);
+/* one line of the reference's cycle table (src/Tallies.cc:123-144, src/Tallies.hh:60-76). */
+int  qsb_mc_format_cycle_row(qsb_mc* mc, int cycle, const uint64_t row[QSB_BAL_COUNT], double flux,
+                             double t_init, double t_track, double t_final, char* buf, uint64_t cap);
+const char* qsb_mc_last_error(qsb_mc* mc);
+
+/* ======================================================================================================
+ * Device context (qsb_*) -- the hot path
+ * ==================================================================================================== */
+typedef struct qsb_ctx qsb_ctx;
+
+typedef struct qsb_options {
+    int32_t  validation;        /* 1: --fmad=false kernels + strict log/sin/cos (bit-exact vs oracle);
+                                   0: fast build (FMA contraction, CUDA libm)                          */
+    int32_t  tracking_mode;     /* 0: history-based persistent kernel (default)                         */
+    uint64_t particle_capacity; /* SoA slots per vault; 0 = derive from nParticles and nuBar            */
+    uint64_t send_capacity;     /* slots per peer send/recv slab; 0 = derive                             */
+    int32_t  threads_per_block; /* 0 = default                                                           */
+    int32_t  blocks_per_sm;     /* 0 = default                                                           */
+} qsb_options;
+
+typedef struct qsb_track_stats {
+    uint64_t n_processed;       /* particle records consumed from the processing vault (incl. secondaries) */
+    uint64_t n_census;          /* records now in the census vault                                      */
+    uint64_t n_sent;            /* records written to peer send slabs                                   */
+    uint32_t n_launches;        /* kernels launched by this call                                        */
+    float    device_ms;         /* CUDA-event time of the call's stream work                            */
+} qsb_track_stats;
+
+int  qsb_create(int device, const qsb_image* image, double time_step, const qsb_options* opt, qsb_ctx** out);
+int  qsb_destroy(qsb_ctx* ctx);
+/* clearCrossSectionCache + per-cycle flux/balance reset (src/main.cc:101-103, src/Tallies.cc:75-93);
+ * swaps census -> processing on the device when keep_census != 0. */
+int  qsb_cycle_begin(qsb_ctx* ctx, int keep_census);
+/* host AoS vault -> device SoA processing vault (append). */
+int  qsb_put_particles(qsb_ctx* ctx, const qsb_base_particle* aos, uint64_t n);
+/* run all local histories to exhaustion, secondaries included (src/main.cc:163-283 for one rank). */
+int  qsb_track(qsb_ctx* ctx, qsb_track_stats* stats);
+int  qsb_census_count(qsb_ctx* ctx, uint64_t* n);
+int  qsb_get_census(qsb_ctx* ctx, qsb_base_particle* aos, uint64_t cap, uint64_t* n);
+int  qsb_get_balance(qsb_ctx* ctx, uint64_t out[QSB_BAL_COUNT]);
+int  qsb_get_scalar_flux(qsb_ctx* ctx, double* out /* [n_cells][n_groups] */);
+int  qsb_scalar_flux_sum(qsb_ctx* ctx, double* sum);
+/* boundary-particle exchange (src/MC_Facet_Crossing_Event.cc:49-67, src/MC_Particle_Buffer.cc): the
+ * tracker packs leavers into per-peer slabs of qsb_base_particle + direction cosine (160 B records);
+ * the caller moves slabs between ranks (NCCL send/recv) and feeds arrivals back with qsb_put_arrivals. */
+int  qsb_send_counts(qsb_ctx* ctx, uint64_t* counts /* [n_ranks] */);
+int  qsb_send_slab(qsb_ctx* ctx, int peer, void** device_ptr, uint64_t* n_records);
+int  qsb_clear_sends(qsb_ctx* ctx);
+int  qsb_put_arrivals(qsb_ctx* ctx, const void* device_records, uint64_t n_records);
+uint64_t qsb_exchange_record_bytes(void);
+const char* qsb_last_error(qsb_ctx* ctx);
+/* number of kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t qsb_launch_count(qsb_ctx* ctx);
+
+/* ======================================================================================================
+ * Drop-in for cycleTracking(MonteCarlo*) (src/main.cc:138-307) on one rank: processing vault -> device,
+ * track, census + balance + flux sum -> host model.  Host buffers in, host buffers out.
+ * ==================================================================================================== */
+int  qsb_mc_cycle_tracking(qsb_mc* mc, qsb_ctx* ctx, qsb_track_stats* stats);
+
+const char* qsb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSB_H */

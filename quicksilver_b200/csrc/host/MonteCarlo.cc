@@ -1,0 +1,346 @@
+// MonteCarlo.cc -- see MonteCarlo.hh.
+#include "MonteCarlo.hh"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "../qs_rng.h"
+
+namespace qsb {
+
+MonteCarlo::MonteCarlo(const Parameters& p, int rank_, int nRanks_)
+: params(p), rank(rank_), nRanks(nRanks_),
+  nuclearData(p.simulationParams.nGroups, p.simulationParams.eMin, p.simulationParams.eMax),
+  timeStep(p.simulationParams.dt)
+{
+    if (nRanks < 1 || rank < 0 || rank >= nRanks) throw std::runtime_error("bad rank / n_ranks");
+    if (p.simulationParams.nParticles / (uint64_t)nRanks == 0)
+        throw std::runtime_error("not enough particles for each rank");
+    initNuclearData(params, nuclearData, materialDatabase);
+    initMesh(params, materialDatabase, rank, nRanks, ddc, domain);
+    buildImage();
+}
+
+// Flatten mesh + nuclear data into the arrays of qsb_image (see include/qsb.h for the layout).
+void MonteCarlo::buildImage()
+{
+    const int nDom = (int)domain.size();
+    const int nGroups = nuclearData.numGroups;
+    const int nMat = (int)materialDatabase.mat.size();
+    Flat& f = flat;
+    f = Flat();
+
+    f.domainCellOffset.assign(nDom + 1, 0);
+    for (int d = 0; d < nDom; ++d)
+    {
+        f.domainCellOffset[d + 1] = f.domainCellOffset[d] + domain[d].nCells;
+        f.domainGid.push_back(domain[d].globalDomain);
+    }
+    const int nCells = f.domainCellOffset[nDom];
+    for (int d = 0; d < nDom; ++d)
+    {
+        const Domain& D = domain[d];
+        f.planes.insert(f.planes.end(), D.planes.begin(), D.planes.end());
+        f.nodes.insert(f.nodes.end(), D.nodes.begin(), D.nodes.end());
+        f.cellGid.insert(f.cellGid.end(), D.cellGid.begin(), D.cellGid.end());
+        f.cellMaterial.insert(f.cellMaterial.end(), D.material.begin(), D.material.end());
+        f.cellVolume.insert(f.cellVolume.end(), D.volume.begin(), D.volume.end());
+        f.cellId.insert(f.cellId.end(), D.cellId.begin(), D.cellId.end());
+        f.faceEvent.insert(f.faceEvent.end(), D.faceEvent.begin(), D.faceEvent.end());
+        f.faceAdjDomain.insert(f.faceAdjDomain.end(), D.faceAdjDomain.begin(), D.faceAdjDomain.end());
+        f.faceNbrRank.insert(f.faceNbrRank.end(), D.faceNbrRank.begin(), D.faceNbrRank.end());
+        for (int c = 0; c < D.nCells; ++c)
+            for (int face = 0; face < 6; ++face)
+            {
+                const size_t k = (size_t)c * 6 + face;
+                int adj = D.faceAdjCell[k];
+                if (D.faceEvent[k] == QSB_ADJ_TRANSIT_ON)        adj += f.domainCellOffset[D.faceAdjDomain[k]];
+                else if (D.faceEvent[k] != QSB_ADJ_TRANSIT_OFF)  adj = f.domainCellOffset[d] + c;   // boundary: itself
+                f.faceAdjCell.push_back(adj);
+            }
+    }
+
+    // nuclear data
+    f.energies = nuclearData.energies;
+    int maxReact = 1, nIsoTotal = 0;
+    for (const Material& m : materialDatabase.mat)
+    {
+        int n = 0;
+        for (int gid : m.isoGid) n += nuclearData.isotopes[gid].nReactions;
+        if (n > maxReact) maxReact = n;
+        nIsoTotal += (int)m.isoGid.size();
+    }
+    f.xsTotal.assign((size_t)nMat * nGroups, 0.0);
+    f.xsReact.assign((size_t)nMat * nGroups * maxReact, 0.0);
+    f.matReactType.assign((size_t)nMat * maxReact, QSB_REACT_UNDEFINED);
+    for (int mi = 0; mi < nMat; ++mi)
+    {
+        const Material& m = materialDatabase.mat[mi];
+        const int nIso = (int)m.isoGid.size();
+        f.matNIso.push_back(nIso);
+        f.matNReact.push_back(nIso ? nuclearData.isotopes[m.isoGid[0]].nReactions : 0);
+        f.matMass.push_back(m.mass);
+        f.matNuBar.push_back(m.nuBar);
+        const double cellNumberDensity = 1.0;                 // src/MC_Domain.cc:387
+        bool periodic = true;
+        for (int g = 0; g < nGroups; ++g)
+        {
+            // weightedMacroscopicCrossSection: sum over isotopes of af*density*(sum over reactions of sigma)
+            double sum = 0.0;
+            int k = 0;
+            for (int i = 0; i < nIso; ++i)
+            {
+                const int gid = m.isoGid[i];
+                const double af = m.atomFraction[i];
+                if (af == 0.0 || cellNumberDensity == 0.0) sum += 1e-20;
+                else sum += af * cellNumberDensity * nuclearData.totalCrossSection(gid, g);
+                for (int r = 0; r < nuclearData.isotopes[gid].nReactions; ++r, ++k)
+                {
+                    const double v = (af == 0.0 || cellNumberDensity == 0.0) ? 1e-20
+                                     : af * cellNumberDensity * nuclearData.sigmaOf(gid, r, g);
+                    f.xsReact[((size_t)mi * nGroups + g) * maxReact + k] = v;
+                    if (g == 0) f.matReactType[(size_t)mi * maxReact + k] = nuclearData.isotopes[gid].reactionType[r];
+                    const int nr0 = f.matNReact[mi];
+                    if (nuclearData.isotopes[gid].nReactions != nr0 ||
+                        std::memcmp(&v, &f.xsReact[((size_t)mi * nGroups + g) * maxReact + r], 8) != 0 ||
+                        nuclearData.isotopes[gid].reactionType[r] != nuclearData.isotopes[m.isoGid[0]].reactionType[r])
+                        periodic = false;
+                }
+            }
+            f.xsTotal[(size_t)mi * nGroups + g] = sum;
+        }
+        f.matPeriodic.push_back(periodic ? 1 : 0);
+    }
+
+    std::memset(&image, 0, sizeof(image));
+    image.abi_version = QSB_ABI_VERSION;
+    image.n_domains = nDom; image.n_cells = nCells; image.n_groups = nGroups; image.n_materials = nMat;
+    image.n_isotopes = nIsoTotal; image.max_reactions_per_material = maxReact;
+    image.my_rank = rank; image.n_ranks = nRanks;
+    image.global_nx = params.simulationParams.nx; image.global_ny = params.simulationParams.ny; image.global_nz = params.simulationParams.nz;
+    image.global_lx = params.simulationParams.lx; image.global_ly = params.simulationParams.ly; image.global_lz = params.simulationParams.lz;
+    image.domain_cell_offset = f.domainCellOffset.data(); image.domain_gid = f.domainGid.data();
+    image.planes = f.planes.data(); image.nodes = f.nodes.data(); image.cell_gid = f.cellGid.data();
+    image.cell_material = f.cellMaterial.data(); image.cell_volume = f.cellVolume.data(); image.cell_id = f.cellId.data();
+    image.face_event = f.faceEvent.data(); image.face_adj_cell = f.faceAdjCell.data();
+    image.face_adj_domain = f.faceAdjDomain.data(); image.face_nbr_rank = f.faceNbrRank.data();
+    image.energies = f.energies.data(); image.mat_n_isotopes = f.matNIso.data(); image.mat_n_reactions = f.matNReact.data();
+    image.mat_mass = f.matMass.data(); image.mat_nu_bar = f.matNuBar.data(); image.mat_react_type = f.matReactType.data();
+    image.xs_total = f.xsTotal.data(); image.xs_react = f.xsReact.data(); image.mat_periodic = f.matPeriodic.data();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cycleInit
+// ---------------------------------------------------------------------------------------------------
+
+void cycleInit(MonteCarlo& mc)
+{
+    // last cycle's census is this cycle's starting population (src/main.cc:106-110)
+    mc.processing.swap(mc.processed);
+    mc.processed.clear();
+    mc.tallies.balanceTask[QSB_BAL_START] = mc.processing.size();
+    mc.tallies.scalarFluxSum = 0.0;
+    sourceNow(mc);
+    populationControl(mc);
+    rouletteLowWeightParticles(mc);
+}
+
+namespace {
+
+// 6 x signed volume of the tet (p0,p1,p2,apex)  (src/MCT.cc:627-646)
+double tetDet(const double* a, const double* b, const double* c, const Vec3& apex)
+{
+    const double v0x = a[0] - apex.x, v0y = a[1] - apex.y, v0z = a[2] - apex.z;
+    const double v1x = b[0] - apex.x, v1y = b[1] - apex.y, v1z = b[2] - apex.z;
+    const double v2x = c[0] - apex.x, v2y = c[1] - apex.y, v2z = c[2] - apex.z;
+    return v0z * (v1x * v2y - v1y * v2x) + v0y * (v1z * v2x - v1x * v2z) + v0x * (v1y * v2z - v1z * v2y);
+}
+
+// uniform point in the cell: pick one of the 24 centre-apex tets by volume, then fold the unit cube
+// into the tet's barycentric simplex (src/MCT.cc:143-226)
+void generateCoordinate(uint64_t* seed, const double* nodes, double cellVolume, double out[3])
+{
+    const Vec3 center = cellPosition(nodes);
+    const double whichVolume = qs_rng_sample(seed) * 6.0 * cellVolume;
+    double running = 0.0;
+    int facet = -1;
+    const double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    while (running < whichVolume)
+    {
+        ++facet;
+        if (facet == 24) break;
+        p0 = nodes + 3 * kFacetPoints[facet][0];
+        p1 = nodes + 3 * kFacetPoints[facet][1];
+        p2 = nodes + 3 * kFacetPoints[facet][2];
+        running += tetDet(p0, p1, p2, center);
+    }
+    double r1 = qs_rng_sample(seed), r2 = qs_rng_sample(seed), r3 = qs_rng_sample(seed);
+    if (r1 + r2 > 1.0) { r1 = 1.0 - r1; r2 = 1.0 - r2; }
+    if (r2 + r3 > 1.0)           { const double t = r3; r3 = 1.0 - r1 - r2; r2 = 1.0 - t; }
+    else if (r1 + r2 + r3 > 1.0) { const double t = r3; r3 = r1 + r2 + r3 - 1.0; r1 = 1.0 - r2 - t; }
+    const double r4 = 1.0 - r1 - r2 - r3;
+    if (!p0) { out[0] = out[1] = out[2] = 0.0; return; }      // r == 0: the reference bails out with the origin
+    out[0] = (r4 * center.x + r1 * p0[0] + r2 * p1[0] + r3 * p2[0]);
+    out[1] = (r4 * center.y + r1 * p0[1] + r2 * p1[1] + r3 * p2[1]);
+    out[2] = (r4 * center.z + r1 * p0[2] + r2 * p1[2] + r3 * p2[2]);
+}
+
+const double kNeutronRestMassEnergy = 9.395656981095e+2;   // MeV   (src/PhysicalConstants.hh:10-12)
+const double kPi = 3.1415926535897932;
+const double kSpeedOfLight = 2.99792458e+10;               // cm/s
+
+double speedFromEnergy(double e)                            // src/MC_SourceNow.cc:169-177
+{
+    return kSpeedOfLight * std::sqrt(e * (e + 2.0 * (kNeutronRestMassEnergy)) /
+                                     ((e + kNeutronRestMassEnergy) * (e + kNeutronRestMassEnergy)));
+}
+
+} // namespace
+
+void sourceNow(MonteCarlo& mc)
+{
+    const SimulationParameters& sp = mc.params.simulationParams;
+    const double dt = mc.timeStep;
+
+    double localWeight = 0;
+    for (const Domain& d : mc.domain)
+        for (int c = 0; c < d.nCells; ++c)
+            localWeight += d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
+    double totalWeight = localWeight;
+    mc.reduceSum(&totalWeight, 1);
+
+    const double sourceFraction = 0.1;
+    const double weight = totalWeight / (sourceFraction * sp.nParticles);
+    mc.sourceParticleWeight = weight;
+
+    for (size_t di = 0; di < mc.domain.size(); ++di)
+    {
+        Domain& d = mc.domain[di];
+        for (int c = 0; c < d.nCells; ++c)
+        {
+            const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
+            const int n = (int)(cellWeight / weight);
+            for (int i = 0; i < n; ++i)
+            {
+                qsb_base_particle p;
+                std::memset(&p, 0, sizeof(p));
+                uint64_t s = d.sourceTally[c]++ + d.cellId[c];
+                p.random_number_seed = qs_rng_spawn(&s);
+                p.identifier = s;
+
+                generateCoordinate(&p.random_number_seed, &d.nodes[(size_t)c * 42], d.volume[c], p.coordinate);
+
+                // isotropic direction (src/DirectionCosine.cc:5-13)
+                const double gamma = 1.0 - 2.0 * qs_rng_sample(&p.random_number_seed);
+                const double sineGamma = std::sqrt((1.0 - (gamma * gamma)));
+                const double phi = kPi * (2.0 * qs_rng_sample(&p.random_number_seed) - 1.0);
+                const double alpha = sineGamma * std::cos(phi);
+                const double beta = sineGamma * std::sin(phi);
+
+                p.kinetic_energy = (sp.eMax - sp.eMin) * qs_rng_sample(&p.random_number_seed) + sp.eMin;
+                const double speed = speedFromEnergy(p.kinetic_energy);
+                p.velocity[0] = speed * alpha; p.velocity[1] = speed * beta; p.velocity[2] = speed * gamma;
+                p.domain = (int32_t)di; p.cell = c;
+                p.weight = weight;
+                p.num_mean_free_paths = -1.0 * std::log(qs_rng_sample(&p.random_number_seed));
+                p.time_to_census = dt * qs_rng_sample(&p.random_number_seed);
+                p.last_event = QSB_EV_CENSUS;        // MC_Particle's default (src/MC_Base_Particle.hh:259)
+                p.species = 0;
+                mc.processing.push_back(p);
+                mc.tallies.balanceTask[QSB_BAL_SOURCE]++;
+            }
+        }
+    }
+}
+
+void populationControl(MonteCarlo& mc)
+{
+    const SimulationParameters& sp = mc.params.simulationParams;
+    uint64_t target = sp.nParticles;
+    const uint64_t localCount = mc.processing.size();
+    uint64_t globalCount = localCount;
+    double factor = 1.0;
+    if (sp.loadBalance)
+    {
+        target = (uint64_t)std::ceil((double)target / (double)mc.nRanks);
+        if ((int)localCount != 0) factor = (double)target / (double)(int)localCount;
+    }
+    else
+    {
+        mc.reduceSum(&globalCount, 1);
+        factor = (double)target / (double)globalCount;
+    }
+    if (factor == 1.0) return;
+
+    // Every particle decides from its own stream, so the result does not depend on vault order; the
+    // reference walks the vault backwards and swap-erases, here survivors are compacted in place and
+    // split copies are appended behind the original population.
+    ParticleVault& v = mc.processing;
+    Balance& bal = mc.tallies.balanceTask;
+    size_t keep = 0;
+    for (size_t i = 0; i < localCount; ++i)
+    {
+        qsb_base_particle p = v[i];                     // by value: push_back below may reallocate
+        const double r = qs_rng_sample(&p.random_number_seed);
+        if (factor < 1)
+        {
+            if (r > factor) { bal[QSB_BAL_RR]++; continue; }
+            p.weight /= factor;
+            v[keep++] = p;
+        }
+        else
+        {
+            int copies = (int)std::floor(factor);
+            if (r > (factor - copies)) copies--;
+            p.weight /= factor;
+            qsb_base_particle child = p;
+            for (int k = 0; k < copies; ++k)
+            {
+                bal[QSB_BAL_SPLIT]++;
+                child.random_number_seed = qs_rng_spawn(&p.random_number_seed);
+                child.identifier = child.random_number_seed;
+                v.push_back(child);
+            }
+            v[i] = p;
+        }
+    }
+    if (factor < 1) v.resize(keep);
+}
+
+void rouletteLowWeightParticles(MonteCarlo& mc)
+{
+    const double cutoff = mc.params.simulationParams.lowWeightCutoff;
+    if (!(cutoff > 0.0)) return;
+    const double weightCutoff = cutoff * mc.sourceParticleWeight;
+    ParticleVault& v = mc.processing;
+    size_t keep = 0;
+    for (size_t i = 0; i < v.size(); ++i)
+    {
+        qsb_base_particle& p = v[i];
+        if (p.weight <= weightCutoff)
+        {
+            const double r = qs_rng_sample(&p.random_number_seed);
+            if (r <= cutoff) p.weight /= cutoff;
+            else { mc.tallies.balanceTask[QSB_BAL_RR]++; continue; }
+        }
+        if (keep != i) v[keep] = p;
+        ++keep;
+    }
+    v.resize(keep);
+}
+
+void cycleFinalize(MonteCarlo& mc, Balance& row, double& flux)
+{
+    Balance& task = mc.tallies.balanceTask;
+    task[QSB_BAL_END] = mc.processed.size();
+    row = task;
+    mc.reduceSum(row.v, QSB_BAL_COUNT);
+    flux = mc.tallies.scalarFluxSum;
+    mc.reduceSum(&flux, 1);
+    mc.tallies.balanceCumulative.add(row);
+    task.reset();
+    mc.cycle++;
+}
+
+} // namespace qsb

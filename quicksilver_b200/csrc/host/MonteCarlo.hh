@@ -1,0 +1,88 @@
+// MonteCarlo.hh -- owner object of the host model (the reference's MonteCarlo god-object,
+// src/MonteCarlo.hh:18-47) together with its ParticleVault and Tallies, and the host stages that
+// bracket the tracking hot path each cycle: cycleInit (source, population control, roulette) and
+// cycleFinalize (balance reduction and bookkeeping).
+#ifndef QSB_MONTECARLO_HH
+#define QSB_MONTECARLO_HH
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../../include/qsb.h"
+#include "Mesh.hh"
+#include "NuclearData.hh"
+#include "Parameters.hh"
+
+namespace qsb {
+
+// Host-side particle vault: one contiguous AoS of MC_Base_Particle-layout records.  The reference's
+// fixed-size batches (src/ParticleVaultContainer.hh) exist only to bound kernel launches and carry no
+// physics; tallies do not depend on vault order.
+typedef std::vector<qsb_base_particle> ParticleVault;
+
+struct Balance
+{
+    uint64_t v[QSB_BAL_COUNT] = { 0 };
+    uint64_t& operator[](int i) { return v[i]; }
+    const uint64_t& operator[](int i) const { return v[i]; }
+    void add(const Balance& o) { for (int i = 0; i < QSB_BAL_COUNT; ++i) v[i] += o.v[i]; }
+    void reset() { for (int i = 0; i < QSB_BAL_COUNT; ++i) v[i] = 0; }
+};
+
+struct Tallies
+{
+    Balance balanceTask;          // this cycle (replications are summed on the device)
+    Balance balanceCumulative;
+    double  scalarFluxSum = 0.0;  // this cycle, local
+};
+
+class MonteCarlo
+{
+public:
+    MonteCarlo(const Parameters& params, int rank, int nRanks);
+
+    Parameters        params;
+    int               rank, nRanks;
+    NuclearData       nuclearData;
+    MaterialDatabase  materialDatabase;
+    DecompositionInfo ddc;
+    std::vector<Domain> domain;
+    Tallies           tallies;
+    ParticleVault     processing, processed;
+    double            timeStep;
+    int               cycle = 0;
+    double            sourceParticleWeight = 0.0;
+
+    qsb_allreduce_fn  allreduce = nullptr;
+    void*             allreduceUser = nullptr;
+    void reduceSum(double* v, int n) const { if (allreduce && nRanks > 1) allreduce(allreduceUser, v, n, 0); }
+    void reduceSum(uint64_t* v, int n) const { if (allreduce && nRanks > 1) allreduce(allreduceUser, v, n, 1); }
+
+    // the flattened image handed to the device context / oracle; arrays live in `flat`
+    void buildImage();
+    qsb_image image;
+    struct Flat
+    {
+        std::vector<int32_t> domainCellOffset, domainGid, cellGid, cellMaterial, faceAdjCell, faceAdjDomain, faceNbrRank;
+        std::vector<double>  planes, nodes, cellVolume, energies, matMass, matNuBar, xsTotal, xsReact;
+        std::vector<uint64_t> cellId;
+        std::vector<uint8_t> faceEvent, matReactType, matPeriodic;
+        std::vector<int32_t> matNIso, matNReact;
+    } flat;
+
+    std::string lastError;
+};
+
+// src/main.cc:96-121
+void cycleInit(MonteCarlo& mc);
+// src/MC_SourceNow.cc:28-133
+void sourceNow(MonteCarlo& mc);
+// src/PopulationControl.cc:20-122, :127-171
+void populationControl(MonteCarlo& mc);
+void rouletteLowWeightParticles(MonteCarlo& mc);
+// src/main.cc:310-324 + src/Tallies.cc:25-98.  Returns this cycle's global balance and flux sum.
+void cycleFinalize(MonteCarlo& mc, Balance& globalRow, double& globalFlux);
+
+} // namespace qsb
+#endif

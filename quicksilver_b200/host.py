@@ -1,0 +1,122 @@
+"""Host model wrapper: the reference's MonteCarlo object + cycleInit / cycleTracking / cycleFinalize
+(src/main.cc:38-121,310-324) over the qsb_mc_* C ABI.  Tracking itself is done by a DeviceContext
+(quicksilver_b200.device) -- this module never computes a segment."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import BAL, BAL_COUNT, BAL_NAMES, PARTICLE_DTYPE, QsbError
+
+
+class MonteCarlo:
+    """mirror of `MonteCarlo* initMC(const Parameters&)` (src/initMC.cc:53-74) for one rank."""
+
+    def __init__(self, argv, rank=0, n_ranks=1, allreduce=None):
+        self._lib = _capi.lib()
+        argv = ["qs"] + [str(a) for a in argv]
+        arr = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+        self._h = C.c_void_p()
+        rc = self._lib.qsb_mc_create(len(argv), arr, rank, n_ranks, C.byref(self._h))
+        if rc != 0:
+            raise QsbError(rc, (self._lib.qsb_mc_last_error(None) or b"").decode())
+        self.rank, self.n_ranks = rank, n_ranks
+        self._cb = None
+        if allreduce is not None:
+            self.set_allreduce(allreduce)
+        self.image = _capi.Image()
+        self._check(self._lib.qsb_mc_get_image(self._h, C.byref(self.image)))
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise QsbError(rc, (self._lib.qsb_mc_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qsb_mc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_allreduce(self, fn):
+        """fn(numpy array) must sum the array over ranks in place (stand-in for mpiAllreduce)."""
+        def trampoline(_user, buf, count, dtype):
+            ct = C.c_double if dtype == 0 else C.c_uint64
+            fn(np.ctypeslib.as_array(C.cast(buf, C.POINTER(ct)), (count,)))
+        self._cb = _capi.ALLREDUCE_FN(trampoline)
+        self._check(self._lib.qsb_mc_set_allreduce(self._h, self._cb, None))
+
+    def get_int(self, key):
+        v = C.c_int64()
+        self._check(self._lib.qsb_mc_get_int(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def get_double(self, key):
+        v = C.c_double()
+        self._check(self._lib.qsb_mc_get_double(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def print_parameters(self):
+        need = C.c_uint64()
+        self._check(self._lib.qsb_mc_print_parameters(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(self._lib.qsb_mc_print_parameters(self._h, buf, need.value, None))
+        return buf.value.decode()
+
+    # -- the cycle ---------------------------------------------------------------------------------
+    def cycle_init(self):
+        self._check(self._lib.qsb_mc_cycle_init(self._h))
+
+    def processing(self):
+        """the processing vault (tracking input) as a structured numpy array (copy)."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.qsb_mc_processing(self._h, C.byref(ptr), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, dtype=PARTICLE_DTYPE)
+        raw = (C.c_char * (n.value * PARTICLE_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(raw, dtype=PARTICLE_DTYPE).copy()
+
+    def set_tracking_result(self, census, balance, flux_sum):
+        census = np.ascontiguousarray(census, dtype=PARTICLE_DTYPE)
+        bal = np.ascontiguousarray(balance, dtype=np.uint64)
+        assert bal.shape == (BAL_COUNT,)
+        self._check(self._lib.qsb_mc_set_tracking_result(
+            self._h, census.ctypes.data_as(C.c_void_p), len(census),
+            bal.ctypes.data_as(C.POINTER(C.c_uint64)), float(flux_sum)))
+
+    def cycle_tracking(self, ctx):
+        """drop-in for cycleTracking(MonteCarlo*) on one rank: host vault -> device -> host."""
+        stats = _capi.TrackStats()
+        self._check(self._lib.qsb_mc_cycle_tracking(self._h, ctx._h, C.byref(stats)))
+        return stats
+
+    def cycle_finalize(self):
+        row = np.zeros(BAL_COUNT, dtype=np.uint64)
+        flux = C.c_double()
+        self._check(self._lib.qsb_mc_cycle_finalize(self._h, row.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(flux)))
+        return row, flux.value
+
+    def cumulative_balance(self):
+        row = np.zeros(BAL_COUNT, dtype=np.uint64)
+        self._check(self._lib.qsb_mc_cumulative_balance(self._h, row.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return row
+
+    def format_cycle_row(self, cycle, row, flux, t_init=0.0, t_track=0.0, t_final=0.0):
+        buf = C.create_string_buffer(2048)
+        row = np.ascontiguousarray(row, dtype=np.uint64)
+        self._check(self._lib.qsb_mc_format_cycle_row(self._h, cycle, row.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                      flux, t_init, t_track, t_final, buf, 2048))
+        return buf.value.decode()
+
+
+def table_row(row, flux):
+    """[start source rr split absorb scatter fission produce collisn escape census num_seg] + flux:
+    the column order of the reference's cycle table (src/Tallies.hh:60-76)."""
+    order = ("start", "source", "rr", "split", "absorb", "scatter", "fission", "produce", "collision", "escape",
+             "census", "num_segments")
+    return [int(row[BAL[k]]) for k in order], flux

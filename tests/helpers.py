@@ -1,0 +1,112 @@
+"""Shared test helpers: QSD reader (oracle/ref_dump.cc output), oracle binding, golden tables."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from quicksilver_b200 import _capi  # noqa: E402
+from quicksilver_b200._capi import BAL, BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE  # noqa: E402
+
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_QS = os.path.join(ORACLE_DIR, "_ref", "qs")
+REF_DUMP = os.path.join(ORACLE_DIR, "_ref", "qs_dump")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def read_qsd(path):
+    """{name: ndarray} from a QSD1 file written by oracle/ref_dump.cc."""
+    out = {}
+    with open(path, "rb") as f:
+        assert f.read(4) == b"QSD1"
+        while True:
+            head = f.read(4)
+            if not head:
+                break
+            nlen = int(np.frombuffer(head, "<u4")[0])
+            name = f.read(nlen).decode()
+            dtype = f.read(1).decode()
+            count, inner = (int(v) for v in np.frombuffer(f.read(16), "<u8"))
+            np_dtype = {"d": "<f8", "i": "<i4", "u": "<u8", "b": "u1"}[dtype]
+            data = np.frombuffer(f.read(count * inner * np.dtype(np_dtype).itemsize), np_dtype)
+            out[name] = data.reshape(count, inner) if inner != 1 else data
+    return out
+
+
+def particles_from_bytes(arr):
+    return np.ascontiguousarray(arr).view(PARTICLE_DTYPE).reshape(-1)
+
+
+def run_reference_dump(argv, out_dir, particle_cycles=1, threads=4):
+    env = dict(os.environ, QS_DUMP_DIR=out_dir, QS_DUMP_PARTICLE_CYCLES=str(particle_cycles), OMP_NUM_THREADS=str(threads))
+    subprocess.run([REF_DUMP] + [str(a) for a in argv], check=True, env=env, stdout=subprocess.DEVNULL)
+
+
+# ---- oracle binding -----------------------------------------------------------------------------------
+
+class _OracleIO(C.Structure):
+    _fields_ = [("initial", C.c_void_p), ("n_initial", C.c_uint64),
+                ("arrivals", C.c_void_p), ("n_arrivals", C.c_uint64),
+                ("census", C.c_void_p), ("census_cap", C.c_uint64), ("n_census", C.c_uint64),
+                ("sends", C.c_void_p), ("send_rank", C.c_void_p), ("send_cap", C.c_uint64), ("n_sends", C.c_uint64),
+                ("balance", C.c_uint64 * BAL_COUNT), ("flux", C.c_void_p), ("n_processed", C.c_uint64),
+                ("n_retry_moves", C.c_uint64), ("n_forced_collisions", C.c_uint64), ("n_reaction_lookups", C.c_uint64)]
+
+
+_oracle = None
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "liboracle.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", ORACLE_DIR, "liboracle.so"], check=True, stdout=subprocess.DEVNULL)
+        _oracle = C.CDLL(path)
+        _oracle.qso_track.restype = C.c_int
+        _oracle.qso_track.argtypes = [C.POINTER(_capi.Image), C.c_double, C.c_int, C.c_int, C.POINTER(_OracleIO)]
+    return _oracle
+
+
+class OracleResult:
+    pass
+
+
+def oracle_track(image, dt, particles, arrivals=None, strict=False, threads=1, census_cap=None, send_cap=None, want_flux=True):
+    """Run the CPU restatement on a processing vault.  Returns census, sends, balance, flux."""
+    lib = oracle_lib()
+    particles = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+    arrivals = np.zeros(0, EXCHANGE_DTYPE) if arrivals is None else np.ascontiguousarray(arrivals, dtype=EXCHANGE_DTYPE)
+    n_in = len(particles) + len(arrivals)
+    census_cap = census_cap or max(1024, 8 * n_in)
+    send_cap = send_cap or max(1024, 8 * n_in)
+    census = np.zeros(census_cap, PARTICLE_DTYPE)
+    sends = np.zeros(send_cap, EXCHANGE_DTYPE)
+    send_rank = np.zeros(send_cap, np.int32)
+    flux = np.zeros((image.n_cells, image.n_groups)) if want_flux else None
+    io = _OracleIO()
+    io.initial, io.n_initial = particles.ctypes.data, len(particles)
+    io.arrivals, io.n_arrivals = arrivals.ctypes.data, len(arrivals)
+    io.census, io.census_cap = census.ctypes.data, census_cap
+    io.sends, io.send_rank, io.send_cap = sends.ctypes.data, send_rank.ctypes.data, send_cap
+    io.flux = flux.ctypes.data if want_flux else None
+    rc = lib.qso_track(C.byref(image), dt, int(strict), int(threads), C.byref(io))
+    if rc != 0:
+        raise RuntimeError("qso_track failed: %d" % rc)
+    r = OracleResult()
+    r.census = census[:io.n_census].copy()
+    r.sends = sends[:io.n_sends].copy()
+    r.send_rank = send_rank[:io.n_sends].copy()
+    r.balance = np.array(list(io.balance), dtype=np.uint64)
+    r.flux = flux
+    r.n_processed = io.n_processed
+    r.n_retry_moves, r.n_forced_collisions, r.n_reaction_lookups = io.n_retry_moves, io.n_forced_collisions, io.n_reaction_lookups
+    return r
+
+
+def sort_particles(p):
+    return p[np.argsort(p["identifier"], kind="stable")]
