@@ -1,0 +1,201 @@
+#!/usr/bin/env python
+"""bench.py -- Quicksilver figure of merit (segments per second of cycle tracking) on B200.
+
+A "step" is one cycle's pass of the tracking hot path over the cycle's processing vault (the part of
+a cycle the reference times as cycleTracking, src/main.cc:138-307, src/MC_Fast_Timer.cc:97-104); the
+host stages around it (cycleInit / cycleFinalize) run untimed between steps, as in the reference's FOM.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+value : segments / second, device-timed (CUDA events on the tracking stream), vault resident in HBM
+e2e   : the same metric through the drop-in call qsb_mc_cycle_tracking with HOST buffers: host vault ->
+        device, tracking, census + tallies -> host, wall clock around the call
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FOM segments/sec (cycle tracking)"
+UNIT = "segments/s"
+
+# per-GPU weak-scaled workloads: (deck, cells per side per GPU, box length per cell, particles per GPU,
+# algorithmic bytes per segment B_seg)
+WORKLOADS = {
+    "Coral2_P1": dict(deck="Coral2_P1", n=64, cell_len=1.0, particles=10485760, b_seg=2270.0),
+    "Coral2_P2": dict(deck="Coral2_P2", n=44, cell_len=1.0 / 11.0, particles=3407360, b_seg=1930.0),
+    "CTS2": dict(deck="CTS2", n=64, cell_len=1.0, particles=2621440, b_seg=2270.0),
+}
+GRID_LADDER = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# the reference's CPU run is timed on a bounded sample of the same deck: its own literal single-rank size
+REFERENCE_SAMPLE = {
+    "Coral2_P1": dict(n=16, particles=163840),
+    "Coral2_P2": dict(n=11, particles=53240),
+    "CTS2": dict(n=16, particles=40960),
+}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def deck_argv(w, grid, tmpdir, n_steps):
+    """command line of one weak-scaled run: the reference's deck + its CLI size flags."""
+    from quicksilver_b200 import decks
+    gx, gy, gz = grid
+    deck = decks.write_deck(decks.derive(w["deck"], nSteps=n_steps), os.path.join(tmpdir, "%s.inp" % w["deck"]))
+    n = w["n"]
+    argv = ["-i", deck, "-X", n * gx * w["cell_len"], "-Y", n * gy * w["cell_len"], "-Z", n * gz * w["cell_len"],
+            "-x", n * gx, "-y", n * gy, "-z", n * gz, "-I", gx, "-J", gy, "-K", gz, "-n", w["particles"] * gx * gy * gz]
+    return [str(a) for a in argv]
+
+
+def run_reference(workload, steps, warmup, threads=None):
+    """The reference's own CPU implementation (oracle/_ref/qs, built from the unmodified sources) on a
+    bounded sample of the workload: same deck, the reference's literal single-rank size."""
+    from quicksilver_b200 import decks
+    qs = os.path.join(ROOT, "oracle", "_ref", "qs")
+    if not os.path.exists(qs):
+        raise RuntimeError("oracle/_ref/qs missing: run __graft_entry__.build() where /root/reference exists")
+    s = REFERENCE_SAMPLE[workload]
+    w = WORKLOADS[workload]
+    threads = threads or os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        deck = decks.write_deck(decks.derive(w["deck"], nSteps=steps + warmup), os.path.join(tmp, "ref.inp"))
+        n = s["n"]
+        argv = [qs, "-i", deck, "-X", n * w["cell_len"], "-Y", n * w["cell_len"], "-Z", n * w["cell_len"], "-x", n, "-y", n, "-z", n,
+                "-I", 1, "-J", 1, "-K", 1, "-n", s["particles"]]
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        out = subprocess.run([str(a) for a in argv], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        wall = time.time() - t0
+    segs, secs = 0, 0.0
+    for line in out.splitlines():
+        f = line.split()
+        if len(f) == 17 and f[0].isdigit() and int(f[0]) >= warmup:
+            segs += int(f[12])
+            secs += float(f[15])
+    value = segs / secs if secs > 0 else 0.0
+    sample = "%s at %d^3 cells, %d particles, %d cycles timed after %d warm-up (reference's cycleTracking timer)" % (
+        workload, s["n"], s["particles"], steps, warmup)
+    return value, threads, sample, secs, wall
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="Coral2_P1", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fast", type=int, default=1, help="1: fast build kernels (default), 0: validation build")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU problem (testing only; reported in config)")
+    ap.add_argument("--cpu-baseline", type=int, default=1)
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        value, threads, sample, secs, _ = run_reference(args.workload, args.steps, warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "note": "reference CPU OpenMP build, bounded sample of the workload"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    if world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
+    import torch
+    from quicksilver_b200 import driver
+
+    result = driver.run_benchmark(args, warmup, rank, world, local_rank, WORKLOADS, GRID_LADDER, deck_argv, ClockSampler)
+    if rank != 0:
+        return 0
+    peak, peak_src = measured_peak()
+    w = WORKLOADS[args.workload]
+    kernel_s = result["kernel_seconds_max"]
+    achieved = w["b_seg"] * result["segments_rank0"] / result["kernel_seconds_rank0"] / 1e9 if result["kernel_seconds_rank0"] > 0 else 0.0
+    line = {"metric": METRIC, "value": result["segments_total"] / kernel_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": 1e3 * kernel_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": result["config"],
+            "clocks": result["clocks"],
+            "e2e": {"value": result["segments_total"] / result["e2e_seconds_max"], "unit": UNIT,
+                    "h2d_bytes_per_step": result["h2d_bytes_per_step"], "d2h_bytes_per_step": result["d2h_bytes_per_step"]},
+            "gpu_launches": result["gpu_launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": result.get("traffic"), "peak_source": peak_src, "kernel": "track_kernel",
+                         "algorithmic_bytes_per_segment": w["b_seg"]},
+            "balance_check": result["balance_check"]}
+    if args.cpu_baseline and world == 1:
+        try:
+            value, threads, sample, _, wall = run_reference(args.workload, 5, 1)
+            line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
+                                    "wall_s": round(wall, 1)}
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

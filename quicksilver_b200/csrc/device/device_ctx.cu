@@ -1,0 +1,588 @@
+// device_ctx.cu -- qsb_ctx: one GPU's share of the problem (see include/qsb.h, "Device context").
+//
+// Owns: the flattened problem image in HBM (geometry arrays + one contiguous "hot block" of nuclear
+// data covered by a persisting-L2 access-policy window), two SoA particle vaults (processing, census),
+// per-peer send slabs, the scalar-flux array and the control block.  All work is issued on one
+// non-blocking stream.  There is no host fallback: any CUDA failure is returned as QSB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+
+using namespace qsb;
+
+namespace {
+
+struct CudaFailure { std::string what; };
+
+void check(cudaError_t e, const char* what)
+{
+    if (e != cudaSuccess) throw CudaFailure{ std::string(what) + ": " + cudaGetErrorString(e) };
+}
+#define QSB_CUDA(call) check((call), #call)
+
+template <typename T>
+T* devAlloc(size_t n, std::vector<void*>& owned)
+{
+    void* p = nullptr;
+    QSB_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+    owned.push_back(p);
+    return static_cast<T*>(p);
+}
+
+template <typename T>
+T* devUpload(const T* host, size_t n, std::vector<void*>& owned)
+{
+    T* p = devAlloc<T>(n, owned);
+    if (n) QSB_CUDA(cudaMemcpy(p, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+}
+
+// ---- small service kernels -------------------------------------------------------------------------
+
+// host AoS records (MC_Base_Particle layout) -> SoA slots [first, first+n) of the processing vault
+__global__ void aos_to_soa_kernel(const qsb_base_particle* __restrict__ in, unsigned long long n, VaultView v,
+                                  unsigned long long first, const int* __restrict__ domain_cell_offset, uint32_t epoch)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const qsb_base_particle b = in[i];
+        const unsigned long long s = first + i;
+        v.x[s] = b.coordinate[0]; v.y[s] = b.coordinate[1]; v.z[s] = b.coordinate[2];
+        v.vx[s] = b.velocity[0]; v.vy[s] = b.velocity[1]; v.vz[s] = b.velocity[2];
+        v.energy[s] = b.kinetic_energy; v.weight[s] = b.weight; v.ttc[s] = b.time_to_census; v.age[s] = b.age;
+        v.nmfp[s] = b.num_mean_free_paths; v.nseg[s] = b.num_segments;
+        v.seed[s] = b.random_number_seed; v.id[s] = b.identifier;
+        v.cell[s] = domain_cell_offset[b.domain] + b.cell;
+        v.tags[s] = make_int4(b.last_event, b.num_collisions, b.breed, b.species);
+        v.dirx[s] = nan; v.diry[s] = nan; v.dirz[s] = nan;
+        v.ready[s] = epoch;
+    }
+}
+
+// arrivals from other ranks (records already in device memory) -> SoA slots, direction cosine kept
+__global__ void arrivals_to_soa_kernel(const ExchangeRecord* __restrict__ in, unsigned long long n, VaultView v,
+                                       unsigned long long first, const int* __restrict__ domain_cell_offset, uint32_t epoch)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const ExchangeRecord r = in[i];
+        const qsb_base_particle& b = r.p;
+        const unsigned long long s = first + i;
+        v.x[s] = b.coordinate[0]; v.y[s] = b.coordinate[1]; v.z[s] = b.coordinate[2];
+        v.vx[s] = b.velocity[0]; v.vy[s] = b.velocity[1]; v.vz[s] = b.velocity[2];
+        v.energy[s] = b.kinetic_energy; v.weight[s] = b.weight; v.ttc[s] = b.time_to_census; v.age[s] = b.age;
+        v.nmfp[s] = b.num_mean_free_paths; v.nseg[s] = b.num_segments;
+        v.seed[s] = b.random_number_seed; v.id[s] = b.identifier;
+        v.cell[s] = domain_cell_offset[b.domain] + b.cell;
+        v.tags[s] = make_int4(b.last_event, b.num_collisions, b.breed, b.species);
+        v.dirx[s] = r.dir[0]; v.diry[s] = r.dir[1]; v.dirz[s] = r.dir[2];
+        __threadfence();
+        v.ready[s] = epoch;
+    }
+}
+
+// census vault SoA -> AoS records for the host
+__global__ void soa_to_aos_kernel(VaultView v, unsigned long long first, unsigned long long n, qsb_base_particle* __restrict__ out,
+                                  const int* __restrict__ domain_cell_offset, int n_domains)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const unsigned long long s = first + i;
+        qsb_base_particle b;
+        b.coordinate[0] = v.x[s]; b.coordinate[1] = v.y[s]; b.coordinate[2] = v.z[s];
+        b.velocity[0] = v.vx[s]; b.velocity[1] = v.vy[s]; b.velocity[2] = v.vz[s];
+        b.kinetic_energy = v.energy[s]; b.weight = v.weight[s]; b.time_to_census = v.ttc[s]; b.age = v.age[s];
+        b.num_mean_free_paths = v.nmfp[s]; b.num_segments = v.nseg[s];
+        b.random_number_seed = v.seed[s]; b.identifier = v.id[s];
+        const int4 t = v.tags[s];
+        b.last_event = t.x; b.num_collisions = t.y; b.breed = t.z; b.species = t.w;
+        const int flat = v.cell[s];
+        int d = 0;
+        while (d + 1 < n_domains && flat >= domain_cell_offset[d + 1]) d++;
+        b.domain = d; b.cell = flat - domain_cell_offset[d];
+        out[i] = b;
+    }
+}
+
+// scalar-flux grand total: fixed-shape two-stage tree, so the result is reproducible run to run
+__global__ void flux_partial_sum_kernel(const double* __restrict__ flux, unsigned long long n, double* __restrict__ partial)
+{
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        acc += flux[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1)
+    {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+} // namespace
+
+struct qsb_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    qsb_options opt{};
+    std::vector<void*> owned;
+    DevImage im{};
+    int n_ranks = 1, my_rank = 0;
+    std::vector<int32_t> host_domain_offset;
+    const int* d_domain_offset = nullptr;
+    VaultView vault[2]{};          // [proc], [census]
+    int proc = 0;
+    ExchangeRecord* sends = nullptr;
+    unsigned long long send_capacity = 0;
+    DevControl* d_ctl = nullptr;
+    DevControl* h_ctl = nullptr;   // pinned mirror
+    double* flux = nullptr;
+    double* flux_partial = nullptr;
+    double* h_partial = nullptr;   // pinned
+    void* staging = nullptr;       // device AoS staging for put/get
+    size_t staging_records = 0;
+    void* h_staging = nullptr;     // pinned host staging (two halves)
+    double dt = 0;
+    unsigned long long host_tail = 0;   // slots written from the host side this cycle
+    unsigned long long ready_prefix = 0;
+    uint32_t epoch = 0;
+    uint64_t launches = 0;
+    int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
+    bool in_cycle = false;
+    std::string error;
+};
+
+namespace {
+
+void allocVault(qsb_ctx* c, VaultView& v, unsigned long long cap)
+{
+    double** f64[] = { &v.x, &v.y, &v.z, &v.vx, &v.vy, &v.vz, &v.energy, &v.weight, &v.ttc, &v.age, &v.nmfp, &v.nseg,
+                       &v.dirx, &v.diry, &v.dirz };
+    for (double** p : f64) *p = devAlloc<double>(cap, c->owned);
+    v.seed = devAlloc<unsigned long long>(cap, c->owned);
+    v.id = devAlloc<unsigned long long>(cap, c->owned);
+    v.cell = devAlloc<int>(cap, c->owned);
+    v.tags = devAlloc<int4>(cap, c->owned);
+    v.ready = devAlloc<uint32_t>(cap, c->owned);
+    QSB_CUDA(cudaMemset(v.ready, 0, cap * sizeof(uint32_t)));
+    v.capacity = cap;
+}
+
+void pushControl(qsb_ctx* c)
+{
+    QSB_CUDA(cudaMemcpyAsync(c->d_ctl, c->h_ctl, sizeof(DevControl), cudaMemcpyHostToDevice, c->stream));
+}
+
+void pullControl(qsb_ctx* c)
+{
+    QSB_CUDA(cudaMemcpyAsync(c->h_ctl, c->d_ctl, sizeof(DevControl), cudaMemcpyDeviceToHost, c->stream));
+    QSB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+template <typename F>
+int guarded(qsb_ctx* c, F&& body)
+{
+    if (!c) return QSB_ERR_ARG;
+    try
+    {
+        QSB_CUDA(cudaSetDevice(c->device));
+        return body();
+    }
+    catch (const CudaFailure& f) { c->error = f.what; return QSB_ERR_CUDA; }
+    catch (const std::exception& e) { c->error = e.what(); return QSB_ERR_INTERNAL; }
+}
+
+thread_local std::string g_create_error;
+
+} // namespace
+
+extern "C" {
+
+const char* qsb_last_error(qsb_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
+uint64_t qsb_launch_count(qsb_ctx* c) { return c ? c->launches : 0; }
+uint64_t qsb_exchange_record_bytes(void) { return sizeof(ExchangeRecord); }
+
+int qsb_create(int device, const qsb_image* image, double time_step, const qsb_options* opt, qsb_ctx** out)
+{
+    if (!image || !out || image->abi_version != QSB_ABI_VERSION) return QSB_ERR_ARG;
+    static_assert(sizeof(ExchangeRecord) == 160, "exchange record layout");
+    *out = nullptr;
+    qsb_ctx* c = new qsb_ctx;
+    try
+    {
+        int n_dev = 0;
+        cudaError_t e = cudaGetDeviceCount(&n_dev);
+        if (e != cudaSuccess || n_dev == 0)
+            throw CudaFailure{ std::string("no CUDA device usable (") + cudaGetErrorString(e) + "); this library has no CPU path" };
+        if (device < 0 || device >= n_dev) throw CudaFailure{ "device index out of range" };
+        QSB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        QSB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw CudaFailure{ std::string("kernels are built for sm_100a only; device is ") + prop.name };
+        c->device = device;
+        c->sm_count = prop.multiProcessorCount;
+        if (opt) c->opt = *opt; else { c->opt = qsb_options{}; c->opt.validation = 1; }
+        c->dt = time_step;
+        c->n_ranks = image->n_ranks; c->my_rank = image->my_rank;
+        if (c->n_ranks > 64) throw CudaFailure{ "at most 64 ranks supported by the control block" };
+        QSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        QSB_CUDA(cudaEventCreate(&c->ev0));
+        QSB_CUDA(cudaEventCreate(&c->ev1));
+
+        // ---- image ----
+        const size_t nc = image->n_cells, ng = image->n_groups, nm = image->n_materials, mr = image->max_reactions_per_material;
+        DevImage& im = c->im;
+        im.n_cells = image->n_cells; im.n_groups = image->n_groups; im.n_materials = image->n_materials;
+        im.max_react = image->max_reactions_per_material; im.n_domains = image->n_domains; im.n_ranks = image->n_ranks;
+        im.planes = reinterpret_cast<const double4*>(devUpload(image->planes, nc * 96, c->owned));
+        im.nodes = devUpload(image->nodes, nc * 42, c->owned);
+        im.face_adj_cell = devUpload(image->face_adj_cell, nc * 6, c->owned);
+        im.face_event = devUpload(image->face_event, nc * 6, c->owned);
+        im.face_adj_domain = devUpload(image->face_adj_domain, nc * 6, c->owned);
+        im.face_nbr_rank = devUpload(image->face_nbr_rank, nc * 6, c->owned);
+        im.cell_material = devUpload(image->cell_material, nc, c->owned);
+        im.domain_cell_offset = devUpload(image->domain_cell_offset, (size_t)image->n_domains + 1, c->owned);
+        c->d_domain_offset = im.domain_cell_offset;
+        c->host_domain_offset.assign(image->domain_cell_offset, image->domain_cell_offset + image->n_domains + 1);
+
+        // hot block: energies | xs_total | xs_react | material records, one allocation, 256-byte sub-alignment
+        auto pad = [](size_t b) { return (b + 255) & ~size_t(255); };
+        const size_t b_energy = pad((ng + 1) * 8), b_total = pad(nm * ng * 8), b_react = pad(nm * ng * mr * 8);
+        const size_t b_mass = pad(nm * 8), b_nubar = pad(nm * 8), b_niso = pad(nm * 4), b_nreact = pad(nm * 4);
+        const size_t b_rtype = pad(nm * mr), b_periodic = pad(nm);
+        const size_t hot_bytes = b_energy + b_total + b_react + b_mass + b_nubar + b_niso + b_nreact + b_rtype + b_periodic;
+        char* hot = devAlloc<char>(hot_bytes, c->owned);
+        std::vector<char> h(hot_bytes, 0);
+        size_t o = 0;
+        auto place = [&](const void* src, size_t bytes, size_t padded) { std::memcpy(h.data() + o, src, bytes); char* p = hot + o; o += padded; return p; };
+        im.energies = (const double*)place(image->energies, (ng + 1) * 8, b_energy);
+        im.xs_total = (const double*)place(image->xs_total, nm * ng * 8, b_total);
+        im.xs_react = (const double*)place(image->xs_react, nm * ng * mr * 8, b_react);
+        im.mat_mass = (const double*)place(image->mat_mass, nm * 8, b_mass);
+        im.mat_nu_bar = (const double*)place(image->mat_nu_bar, nm * 8, b_nubar);
+        im.mat_n_iso = (const int*)place(image->mat_n_isotopes, nm * 4, b_niso);
+        im.mat_n_react = (const int*)place(image->mat_n_reactions, nm * 4, b_nreact);
+        im.mat_react_type = (const uint8_t*)place(image->mat_react_type, nm * mr, b_rtype);
+        im.mat_periodic = (const uint8_t*)place(image->mat_periodic, nm, b_periodic);
+        QSB_CUDA(cudaMemcpy(hot, h.data(), hot_bytes, cudaMemcpyHostToDevice));
+
+        // pin the hot block in L2 (126 MB on B200): persisting carve-out + access-policy window on our stream
+        {
+            size_t want = std::min<size_t>(hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
+            if (want > 0 && prop.accessPolicyMaxWindowSize > 0)
+            {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+                cudaStreamAttrValue attr{};
+                attr.accessPolicyWindow.base_ptr = hot;
+                attr.accessPolicyWindow.num_bytes = std::min<size_t>(hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+                attr.accessPolicyWindow.hitRatio = 1.0f;
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+                cudaGetLastError();     // the window is a hint; failure to set it is not an error
+            }
+        }
+
+        // ---- vaults, slabs, tallies ----
+        unsigned long long cap = c->opt.particle_capacity;
+        if (cap == 0) cap = 1ull << 20;
+        allocVault(c, c->vault[0], cap);
+        allocVault(c, c->vault[1], cap);
+        c->send_capacity = c->n_ranks > 1 ? (c->opt.send_capacity ? c->opt.send_capacity : std::max<unsigned long long>(cap / 8, 4096)) : 1;
+        c->sends = devAlloc<ExchangeRecord>((size_t)c->n_ranks * c->send_capacity, c->owned);
+        c->flux = devAlloc<double>(nc * ng, c->owned);
+        QSB_CUDA(cudaMemset(c->flux, 0, nc * ng * sizeof(double)));
+        c->flux_partial = devAlloc<double>(1024, c->owned);
+        c->d_ctl = devAlloc<DevControl>(1, c->owned);
+        QSB_CUDA(cudaMallocHost((void**)&c->h_ctl, sizeof(DevControl)));
+        QSB_CUDA(cudaMallocHost((void**)&c->h_partial, 1024 * sizeof(double)));
+        std::memset(c->h_ctl, 0, sizeof(DevControl));
+        c->staging_records = 1u << 20;
+        c->staging = devAlloc<char>(c->staging_records * sizeof(qsb_base_particle), c->owned);
+        QSB_CUDA(cudaMallocHost(&c->h_staging, c->staging_records * sizeof(qsb_base_particle)));
+
+        // ---- launch shape: persistent grid, resident blocks per SM from the occupancy calculator ----
+        c->block = c->opt.threads_per_block > 0 ? c->opt.threads_per_block : 128;
+        if (c->opt.validation) track_kernel_attributes_validation(&c->regs, &c->blocks_per_sm, c->block);
+        else                   track_kernel_attributes_fast(&c->regs, &c->blocks_per_sm, c->block);
+        check(cudaGetLastError(), "kernel attributes (is the sm_100a image loadable on this device?)");
+        if (c->blocks_per_sm < 1) throw CudaFailure{ "tracking kernel cannot be resident on this device" };
+        if (c->opt.blocks_per_sm > 0) c->blocks_per_sm = std::min(c->blocks_per_sm, c->opt.blocks_per_sm);
+        c->grid = c->sm_count * c->blocks_per_sm;
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    catch (const CudaFailure& f)
+    {
+        g_create_error = f.what;
+        for (void* p : c->owned) cudaFree(p);
+        delete c;
+        return QSB_ERR_CUDA;
+    }
+    *out = c;
+    return QSB_OK;
+}
+
+int qsb_destroy(qsb_ctx* c)
+{
+    if (!c) return QSB_ERR_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->owned) cudaFree(p);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    if (c->h_partial) cudaFreeHost(c->h_partial);
+    if (c->h_staging) cudaFreeHost(c->h_staging);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return QSB_OK;
+}
+
+int qsb_cycle_begin(qsb_ctx* c, int keep_census)
+{
+    return guarded(c, [&]() {
+        c->epoch++;
+        unsigned long long carried = 0;
+        if (keep_census && c->in_cycle)
+        {
+            pullControl(c);
+            carried = std::min<unsigned long long>(c->h_ctl->census_count, c->vault[1 - c->proc].capacity);
+            c->proc = 1 - c->proc;                           // last cycle's census becomes the processing vault
+            // its slots carry an older epoch: they are covered by ready_prefix instead
+        }
+        std::memset(c->h_ctl, 0, sizeof(DevControl));
+        c->h_ctl->epoch = c->epoch;
+        c->h_ctl->tail = carried;
+        c->host_tail = carried;
+        c->ready_prefix = carried;
+        pushControl(c);
+        QSB_CUDA(cudaMemsetAsync(c->flux, 0, (size_t)c->im.n_cells * c->im.n_groups * sizeof(double), c->stream));
+        c->in_cycle = true;
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_put_particles(qsb_ctx* c, const qsb_base_particle* aos, uint64_t n)
+{
+    if (n && !aos) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->in_cycle) { c->error = "qsb_put_particles before qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        VaultView& v = c->vault[c->proc];
+        if (c->host_tail != c->h_ctl->tail)
+        { c->error = "qsb_put_particles after tracking started: use qsb_put_arrivals"; return (int)QSB_ERR_STATE; }
+        if (c->host_tail + n > v.capacity)
+        { c->error = "processing vault capacity exceeded by qsb_put_particles"; return (int)QSB_ERR_CAPACITY; }
+        // chunked: pageable host -> pinned -> device AoS staging -> SoA scatter kernel
+        const size_t chunk = c->staging_records;
+        for (uint64_t done = 0; done < n; done += chunk)
+        {
+            const uint64_t m = std::min<uint64_t>(chunk, n - done);
+            QSB_CUDA(cudaStreamSynchronize(c->stream));      // pinned staging buffer is free again
+            std::memcpy(c->h_staging, aos + done, m * sizeof(qsb_base_particle));
+            QSB_CUDA(cudaMemcpyAsync(c->staging, c->h_staging, m * sizeof(qsb_base_particle), cudaMemcpyHostToDevice, c->stream));
+            const int grid = (int)std::min<uint64_t>((m + 255) / 256, 4096);
+            aos_to_soa_kernel<<<grid, 256, 0, c->stream>>>((const qsb_base_particle*)c->staging, m, v, c->host_tail + done,
+                                                           c->d_domain_offset, c->epoch);
+            c->launches++;
+        }
+        QSB_CUDA(cudaGetLastError());
+        c->host_tail += n;
+        c->ready_prefix = c->host_tail;
+        c->h_ctl->tail = c->host_tail;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_put_arrivals(qsb_ctx* c, const void* device_records, uint64_t n)
+{
+    if (n && !device_records) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->in_cycle) { c->error = "qsb_put_arrivals before qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        if (n == 0) return (int)QSB_OK;
+        pullControl(c);
+        VaultView& v = c->vault[c->proc];
+        const unsigned long long first = c->h_ctl->tail;
+        if (first + n > v.capacity) { c->error = "processing vault capacity exceeded by arrivals"; return (int)QSB_ERR_CAPACITY; }
+        const int grid = (int)std::min<uint64_t>((n + 255) / 256, 4096);
+        arrivals_to_soa_kernel<<<grid, 256, 0, c->stream>>>((const ExchangeRecord*)device_records, n, v, first, c->d_domain_offset, c->epoch);
+        c->launches++;
+        QSB_CUDA(cudaGetLastError());
+        c->h_ctl->tail = first + n;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
+{
+    return guarded(c, [&]() {
+        if (!c->in_cycle) { c->error = "qsb_track before qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        TrackArgs a;
+        a.im = c->im;
+        a.proc = c->vault[c->proc];
+        a.census = c->vault[1 - c->proc];
+        a.sends = c->sends; a.send_capacity = c->send_capacity;
+        a.ctl = c->d_ctl; a.flux = c->flux; a.dt = c->dt; a.ready_prefix = c->ready_prefix;
+        uint32_t n_launch = 0;
+        QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        for (;;)
+        {
+            if (c->opt.validation) launch_track_validation(a, c->grid, c->block, c->stream);
+            else                   launch_track_fast(a, c->grid, c->block, c->stream);
+            QSB_CUDA(cudaGetLastError());
+            ++n_launch; c->launches++;
+            pullControl(c);
+            const unsigned long long tail = std::min<unsigned long long>(c->h_ctl->tail, a.proc.capacity);
+            if (c->h_ctl->head >= tail) break;     // every allocated slot has been consumed
+            if (n_launch > 100000) { c->error = "tracking did not converge"; return (int)QSB_ERR_INTERNAL; }
+        }
+        QSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        QSB_CUDA(cudaEventSynchronize(c->ev1));
+        float ms = 0;
+        QSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (stats)
+        {
+            stats->n_processed = c->h_ctl->head;
+            stats->n_census = c->h_ctl->census_count;
+            unsigned long long sent = 0;
+            for (int r = 0; r < c->n_ranks; ++r) sent += c->h_ctl->send_count[r];
+            stats->n_sent = sent;
+            stats->n_launches = n_launch;
+            stats->device_ms = ms;
+        }
+        if (c->h_ctl->overflow)
+        {
+            char msg[160];
+            std::snprintf(msg, sizeof msg, "fixed-capacity storage overflowed (mask %u: 1 processing vault, 2 census vault, 4 send slab); "
+                          "raise qsb_options.particle_capacity / send_capacity", c->h_ctl->overflow);
+            c->error = msg;
+            return (int)QSB_ERR_CAPACITY;
+        }
+        if (c->h_ctl->bad_reaction)
+        { c->error = "a collision selected no reaction (cross-section table inconsistent)"; return (int)QSB_ERR_INTERNAL; }
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_census_count(qsb_ctx* c, uint64_t* n)
+{
+    if (!n) return QSB_ERR_ARG;
+    return guarded(c, [&]() { pullControl(c); *n = c->h_ctl->census_count; return (int)QSB_OK; });
+}
+
+int qsb_get_census(qsb_ctx* c, qsb_base_particle* aos, uint64_t cap, uint64_t* n_out)
+{
+    if (!n_out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        pullControl(c);
+        const uint64_t n = c->h_ctl->census_count;
+        *n_out = n;
+        if (n > cap || (n && !aos)) { c->error = "census buffer too small"; return (int)QSB_ERR_CAPACITY; }
+        const VaultView& v = c->vault[1 - c->proc];
+        const size_t chunk = c->staging_records;
+        for (uint64_t done = 0; done < n; done += chunk)
+        {
+            const uint64_t m = std::min<uint64_t>(chunk, n - done);
+            const int grid = (int)std::min<uint64_t>((m + 255) / 256, 4096);
+            soa_to_aos_kernel<<<grid, 256, 0, c->stream>>>(v, done, m, (qsb_base_particle*)c->staging, c->d_domain_offset, c->im.n_domains);
+            c->launches++;
+            QSB_CUDA(cudaMemcpyAsync(c->h_staging, c->staging, m * sizeof(qsb_base_particle), cudaMemcpyDeviceToHost, c->stream));
+            QSB_CUDA(cudaStreamSynchronize(c->stream));
+            std::memcpy(aos + done, c->h_staging, m * sizeof(qsb_base_particle));
+        }
+        QSB_CUDA(cudaGetLastError());
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_get_balance(qsb_ctx* c, uint64_t out[QSB_BAL_COUNT])
+{
+    if (!out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        pullControl(c);
+        for (int i = 0; i < QSB_BAL_COUNT; ++i) out[i] = c->h_ctl->balance[i];
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_get_scalar_flux(qsb_ctx* c, double* out)
+{
+    if (!out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        QSB_CUDA(cudaMemcpyAsync(out, c->flux, (size_t)c->im.n_cells * c->im.n_groups * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_scalar_flux_sum(qsb_ctx* c, double* sum)
+{
+    if (!sum) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        const unsigned long long n = (unsigned long long)c->im.n_cells * c->im.n_groups;
+        const int blocks = (int)std::min<unsigned long long>(1024, (n + 255) / 256);
+        flux_partial_sum_kernel<<<blocks, 256, 0, c->stream>>>(c->flux, n, c->flux_partial);
+        c->launches++;
+        QSB_CUDA(cudaGetLastError());
+        QSB_CUDA(cudaMemcpyAsync(c->h_partial, c->flux_partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        double s = 0.0;
+        for (int i = 0; i < blocks; ++i) s += c->h_partial[i];
+        *sum = s;
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_send_counts(qsb_ctx* c, uint64_t* counts)
+{
+    if (!counts) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        pullControl(c);
+        for (int r = 0; r < c->n_ranks; ++r) counts[r] = c->h_ctl->send_count[r];
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_send_slab(qsb_ctx* c, int peer, void** device_ptr, uint64_t* n_records)
+{
+    if (!device_ptr || !n_records) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (peer < 0 || peer >= c->n_ranks) return (int)QSB_ERR_ARG;
+        *device_ptr = c->sends + (size_t)peer * c->send_capacity;
+        *n_records = c->h_ctl->send_count[peer];
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_clear_sends(qsb_ctx* c)
+{
+    return guarded(c, [&]() {
+        for (int r = 0; r < 64; ++r) c->h_ctl->send_count[r] = 0;
+        QSB_CUDA(cudaMemsetAsync(c->d_ctl->send_count, 0, sizeof(c->h_ctl->send_count), c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+} // extern "C"

@@ -1,0 +1,91 @@
+// device_types.cuh -- plain structs shared by the device context (device_ctx.cu) and the tracking
+// kernels (track_kernels.cu).  Everything here is a view onto memory owned by qsb_ctx.
+#ifndef QSB_DEVICE_TYPES_CUH
+#define QSB_DEVICE_TYPES_CUH
+
+#include <cstdint>
+#include "../../../include/qsb.h"
+
+namespace qsb {
+
+// read-only problem image in HBM (see include/qsb.h: qsb_image for the meaning of each array)
+struct DevImage
+{
+    int n_cells, n_groups, n_materials, max_react, n_domains, n_ranks;
+    const double4* planes;          // [n_cells*24] {A,B,C,D}, 32-byte aligned records
+    const double*  nodes;           // [n_cells*42]
+    const int*     face_adj_cell;   // [n_cells*6]
+    const uint8_t* face_event;      // [n_cells*6]
+    const int*     face_adj_domain; // [n_cells*6]
+    const int*     face_nbr_rank;   // [n_cells*6]
+    const int*     cell_material;   // [n_cells]
+    const int*     domain_cell_offset; // [n_domains+1]
+    // "hot block": one contiguous allocation covered by the persisting-L2 access-policy window
+    const double*  energies;        // [n_groups+1]
+    const double*  xs_total;        // [n_materials*n_groups]
+    const double*  xs_react;        // [n_materials*n_groups*max_react]
+    const double*  mat_mass;        // [n_materials]
+    const double*  mat_nu_bar;      // [n_materials]
+    const int*     mat_n_iso;       // [n_materials]
+    const int*     mat_n_react;     // [n_materials]
+    const uint8_t* mat_react_type;  // [n_materials*max_react]
+    const uint8_t* mat_periodic;    // [n_materials]
+};
+
+// SoA particle vault: one array per MC_Base_Particle field (src/MC_Base_Particle.hh:75-92), cell is the
+// FLAT cell index, dir* carry the direction cosine of arrivals from other ranks (NaN = derive from
+// velocity, the reference's MC_Particle(const MC_Base_Particle&) behaviour).
+struct VaultView
+{
+    double *x, *y, *z, *vx, *vy, *vz, *energy, *weight, *ttc, *age, *nmfp, *nseg;
+    double *dirx, *diry, *dirz;
+    unsigned long long *seed, *id;
+    int *cell;
+    int4 *tags;                     // {last_event, num_collisions, breed, species}
+    uint32_t *ready;                // == epoch once the slot is fully written (processing vault only)
+    unsigned long long capacity;
+};
+
+// exchange record for boundary-crossing particles: MC_Base_Particle + direction cosine (160 bytes)
+struct ExchangeRecord
+{
+    qsb_base_particle p;
+    double dir[3];
+};
+
+// queue control + tallies, one struct in device memory so a single small copy brings the state back
+struct DevControl
+{
+    unsigned long long head;            // next unclaimed slot of the processing vault
+    unsigned long long tail;            // slots allocated (initial + arrivals + secondaries)
+    unsigned long long census_count;
+    unsigned long long balance[QSB_BAL_COUNT];
+    unsigned long long n_lookups;       // diagnostics
+    unsigned int overflow;              // bit0 processing vault, bit1 census vault, bit2 send slab
+    unsigned int bad_reaction;          // collisions where no reaction was selected (reference: unreachable)
+    unsigned int epoch;
+    unsigned int pad;
+    unsigned long long send_count[64];  // per peer rank
+};
+
+struct TrackArgs
+{
+    DevImage im;
+    VaultView proc;
+    VaultView census;
+    ExchangeRecord* sends;              // [n_ranks][send_capacity]
+    unsigned long long send_capacity;
+    DevControl* ctl;
+    double* flux;                       // [n_cells][n_groups]
+    double dt;
+    unsigned long long ready_prefix;    // slots below this index were written by the host side
+};
+
+// launchers implemented twice in track_kernels.cu (validation: --fmad=false + strict math; fast)
+void launch_track_validation(const TrackArgs& a, int grid, int block, cudaStream_t s);
+void launch_track_fast(const TrackArgs& a, int grid, int block, cudaStream_t s);
+void track_kernel_attributes_validation(int* regs, int* max_blocks_per_sm, int block);
+void track_kernel_attributes_fast(int* regs, int* max_blocks_per_sm, int block);
+
+} // namespace qsb
+#endif

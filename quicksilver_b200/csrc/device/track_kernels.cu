@@ -1,0 +1,631 @@
+// track_kernels.cu -- the cycle-tracking hot path on sm_100a.
+//
+// One persistent kernel follows particle histories to census / absorption / escape / rank exit
+// (reference: CycleTrackingGuts + CycleTrackingFunction, src/CycleTracking.cc:15-119).  Each lane owns one
+// in-flight particle held in registers; when a history ends the lane refills from the processing
+// vault (warp-aggregated claim), so warps stay full until the vault drains.  Fission secondaries are
+// appended to the same vault and picked up by whichever lane refills next; the fissioning parent is
+// "re-queued" in place (the reference sends it through the extra vault and MC_Load_Particle again,
+// src/CollisionEvent.cc:137-142 -- here the same reload transform is applied in registers).
+//
+// This file is compiled twice (csrc/Makefile): QSB_VALIDATION=1 with --fmad=false and the portable
+// log/sin/cos of qs_strict_math.h (bit-comparable with the CPU oracle), QSB_VALIDATION=0 with FMA
+// contraction and the CUDA math library.
+//
+// Reference map: segment outcome  src/MC_Segment_Outcome.cc:31-226
+//                nearest facet    src/MCT.cc:87-137,280-395,436-621
+//                collision        src/CollisionEvent.cc:25-148, src/NuclearData.cc:54-88,208-227
+//                facet crossing   src/MC_Facet_Crossing_Event.cc:25-70, src/MCT.cc:401-429
+//                tallies          src/Tallies.hh:36-100,351-354
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "device_types.cuh"
+#include "../qs_rng.h"
+#include "../qs_strict_math.h"
+
+#ifndef QSB_VALIDATION
+#define QSB_VALIDATION 1
+#endif
+
+namespace qsb {
+namespace {
+
+constexpr double kNeutronRestMassEnergy = 9.395656981095e+2;
+constexpr double kSpeedOfLight = 2.99792458e+10;
+constexpr double kTinyDouble = 1.0e-13;
+constexpr double kSmallDouble = 1.0e-10;
+constexpr double kHugeDouble = 1.0e+75;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// facet -> 3 of the cell's 14 points, and facet -> matching facet of the face neighbour (src/MC_Domain.cc:41-50)
+__constant__ int8_t c_facet_points[24][4] = {
+    {1, 3, 8, 0},  {3, 7, 8, 0},  {7, 5, 8, 0},  {5, 1, 8, 0},  {0, 4, 9, 0},  {4, 6, 9, 0},  {6, 2, 9, 0},  {2, 0, 9, 0},
+    {3, 2, 10, 0}, {2, 6, 10, 0}, {6, 7, 10, 0}, {7, 3, 10, 0}, {0, 1, 11, 0}, {1, 5, 11, 0}, {5, 4, 11, 0}, {4, 0, 11, 0},
+    {4, 5, 12, 0}, {5, 7, 12, 0}, {7, 6, 12, 0}, {6, 4, 12, 0}, {0, 2, 13, 0}, {2, 3, 13, 0}, {3, 1, 13, 0}, {1, 0, 13, 0} };
+__constant__ int8_t c_opposing_facet[24] = { 7, 6, 5, 4, 3, 2, 1, 0, 12, 15, 14, 13, 8, 11, 10, 9, 20, 23, 22, 21, 16, 19, 18, 17 };
+
+struct Particle
+{
+    double x, y, z, vx, vy, vz, alpha, beta, gamma;
+    double energy, weight, ttc, age, nmfp, nseg, total_xs;
+    uint64_t seed, id;
+    int cell, facet, group;
+    int last_event, num_collisions, breed, species;
+};
+
+struct Counters     // per-thread balance tallies, flushed once per kernel (src/Tallies.hh:36-100)
+{
+    unsigned int segments, collisions, scatters, absorbs, fissions, produced, escapes, census, lookups;
+};
+
+// one facet plane {A,B,C,D}: two 16-byte read-only loads
+__device__ __forceinline__ double4 load_plane(const double4* __restrict__ p)
+{
+    const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__device__ __forceinline__ double m_log(double x)
+{
+#if QSB_VALIDATION
+    return qs_strict_log(x);
+#else
+    return log(x);
+#endif
+}
+
+__device__ __forceinline__ void m_sincos(double phi, double* s, double* c)
+{
+#if QSB_VALIDATION
+    qs_strict_sincos(phi, s, c);
+#else
+    sincos(phi, s, c);
+#endif
+}
+
+// src/NuclearData.cc:208-227
+__device__ __forceinline__ int energy_group(const DevImage& im, double energy)
+{
+    const int n = im.n_groups + 1;
+    const double* __restrict__ e = im.energies;
+    if (energy <= __ldg(e)) return 0;
+    if (energy > __ldg(e + n - 1)) return n - 1;
+    int high = n - 1, low = 0;
+    while (high != low + 1)
+    {
+        const int mid = (high + low) / 2;
+        if (energy < __ldg(e + mid)) high = mid; else low = mid;
+    }
+    return low;
+}
+
+// MC_Load_Particle + MC_Particle(const MC_Base_Particle&): src/MC_Load_Particle.cc:11-29,
+// src/MC_Base_Particle.hh:287-331
+__device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p, double dt, bool derive_direction)
+{
+    if (derive_direction)
+    {
+        const double speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+        const double factor = 1.0 / speed;
+        p.alpha = factor * p.vx; p.beta = factor * p.vy; p.gamma = factor * p.vz;
+    }
+    if (p.ttc <= 0.0) p.ttc += dt;
+    if (p.age < 0.0) p.age = 0.0;
+    p.group = energy_group(im, p.energy);
+}
+
+__device__ __forceinline__ void load_particle(const TrackArgs& a, unsigned long long i, Particle& p)
+{
+    const VaultView& v = a.proc;
+    p.x = __ldcg(v.x + i); p.y = __ldcg(v.y + i); p.z = __ldcg(v.z + i);
+    p.vx = __ldcg(v.vx + i); p.vy = __ldcg(v.vy + i); p.vz = __ldcg(v.vz + i);
+    p.energy = __ldcg(v.energy + i); p.weight = __ldcg(v.weight + i); p.ttc = __ldcg(v.ttc + i);
+    p.age = __ldcg(v.age + i); p.nmfp = __ldcg(v.nmfp + i); p.nseg = __ldcg(v.nseg + i);
+    p.seed = (uint64_t)__ldcg(v.seed + i); p.id = (uint64_t)__ldcg(v.id + i);
+    p.cell = __ldcg(v.cell + i);
+    const int4 t = __ldcg(v.tags + i);
+    p.last_event = t.x; p.num_collisions = t.y; p.breed = t.z; p.species = t.w;
+    p.alpha = __ldcg(v.dirx + i); p.beta = __ldcg(v.diry + i); p.gamma = __ldcg(v.dirz + i);
+    p.facet = 0; p.total_xs = 0.0;
+    reload_transform(a.im, p, a.dt, p.alpha != p.alpha);
+}
+
+__device__ __forceinline__ void store_particle(const VaultView& v, unsigned long long i, const Particle& p, bool with_direction)
+{
+    __stcg(v.x + i, p.x); __stcg(v.y + i, p.y); __stcg(v.z + i, p.z);
+    __stcg(v.vx + i, p.vx); __stcg(v.vy + i, p.vy); __stcg(v.vz + i, p.vz);
+    __stcg(v.energy + i, p.energy); __stcg(v.weight + i, p.weight); __stcg(v.ttc + i, p.ttc);
+    __stcg(v.age + i, p.age); __stcg(v.nmfp + i, p.nmfp); __stcg(v.nseg + i, p.nseg);
+    __stcg(v.seed + i, (unsigned long long)p.seed); __stcg(v.id + i, (unsigned long long)p.id);
+    __stcg(v.cell + i, p.cell);
+    __stcg(v.tags + i, make_int4(p.last_event, p.num_collisions, p.breed, p.species));
+    if (v.dirx)
+    {
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        __stcg(v.dirx + i, with_direction ? p.alpha : nan);
+        __stcg(v.diry + i, with_direction ? p.beta : nan);
+        __stcg(v.dirz + i, with_direction ? p.gamma : nan);
+    }
+}
+
+// ---- nearest facet ---------------------------------------------------------------------------------
+
+// ray / triangle test of one facet: src/MCT.cc:280-395
+__device__ __forceinline__ double distance_to_segment(double plane_tolerance, double dot, const double4 pl,
+                                                      const double* __restrict__ n0, const double* __restrict__ n1,
+                                                      const double* __restrict__ n2, const Particle& p)
+{
+    const double bb_tol = 1e-9;
+    const double numerator = -1.0 * (pl.x * p.x + pl.y * p.y + pl.z * p.z + pl.w);
+    if (numerator < 0.0 && numerator * numerator > plane_tolerance) return kHugeDouble;
+
+    const double distance = numerator / dot;
+    const double ix = p.x + distance * p.alpha;
+    const double iy = p.y + distance * p.beta;
+    const double iz = p.z + distance * p.gamma;
+
+    const double ax = __ldg(n0), ay = __ldg(n0 + 1), az = __ldg(n0 + 2);
+    const double bx = __ldg(n1), by = __ldg(n1 + 1), bz = __ldg(n1 + 2);
+    const double cx = __ldg(n2), cy = __ldg(n2 + 1), cz = __ldg(n2 + 2);
+
+#define QSB_BELOW(a_, b_, c_, i_) ((a_) > (i_) + bb_tol && (b_) > (i_) + bb_tol && (c_) > (i_) + bb_tol)
+#define QSB_ABOVE(a_, b_, c_, i_) ((a_) < (i_) - bb_tol && (b_) < (i_) - bb_tol && (c_) < (i_) - bb_tol)
+#define QSB_CROSS(ax_, ay_, bx_, by_, cx_, cy_) (((bx_) - (ax_)) * ((cy_) - (ay_)) - ((by_) - (ay_)) * ((cx_) - (ax_)))
+
+    double cross0 = 0, cross1 = 0, cross2 = 0;
+    if (pl.z < -0.5 || pl.z > 0.5)
+    {
+        if (QSB_BELOW(ax, bx, cx, ix) || QSB_ABOVE(ax, bx, cx, ix) || QSB_BELOW(ay, by, cy, iy) || QSB_ABOVE(ay, by, cy, iy))
+            return kHugeDouble;
+        cross1 = QSB_CROSS(ax, ay, bx, by, ix, iy);
+        cross2 = QSB_CROSS(bx, by, cx, cy, ix, iy);
+        cross0 = QSB_CROSS(cx, cy, ax, ay, ix, iy);
+    }
+    else if (pl.y < -0.5 || pl.y > 0.5)
+    {
+        if (QSB_BELOW(ax, bx, cx, ix) || QSB_ABOVE(ax, bx, cx, ix) || QSB_BELOW(az, bz, cz, iz) || QSB_ABOVE(az, bz, cz, iz))
+            return kHugeDouble;
+        cross1 = QSB_CROSS(az, ax, bz, bx, iz, ix);
+        cross2 = QSB_CROSS(bz, bx, cz, cx, iz, ix);
+        cross0 = QSB_CROSS(cz, cx, az, ax, iz, ix);
+    }
+    else if (pl.x < -0.5 || pl.x > 0.5)
+    {
+        if (QSB_BELOW(az, bz, cz, iz) || QSB_ABOVE(az, bz, cz, iz) || QSB_BELOW(ay, by, cy, iy) || QSB_ABOVE(ay, by, cy, iy))
+            return kHugeDouble;
+        cross1 = QSB_CROSS(ay, az, by, bz, iy, iz);
+        cross2 = QSB_CROSS(by, bz, cy, cz, iy, iz);
+        cross0 = QSB_CROSS(cy, cz, ay, az, iy, iz);
+    }
+#undef QSB_BELOW
+#undef QSB_ABOVE
+#undef QSB_CROSS
+
+    const double cross_tol = 1e-9 * fabs(cross0 + cross1 + cross2);
+    if ((cross0 > -cross_tol && cross1 > -cross_tol && cross2 > -cross_tol) ||
+        (cross0 <  cross_tol && cross1 <  cross_tol && cross2 <  cross_tol))
+        return distance;
+    return kHugeDouble;
+}
+
+// all 24 facets of the cell, nearest positive hit, fallback + retry nudge: src/MCT.cc:436-621, :87-137
+__device__ __noinline__ void nearest_facet(const DevImage& im, Particle& p, int& out_facet, double& out_distance)
+{
+    const double4* __restrict__ planes = im.planes + (size_t)p.cell * 24;
+    const double* __restrict__ nodes = im.nodes + (size_t)p.cell * 42;
+    int iteration = 0;
+    double move_factor = 0.5 * kSmallDouble;
+    int nf_facet; double nf_distance;
+    for (;;)
+    {
+        const double plane_tolerance = 1e-16 * (p.x * p.x + p.y * p.y + p.z * p.z);
+        nf_facet = 0; nf_distance = 1e80;
+        int neg_facet = 0; double neg_distance = -kHugeDouble;
+#pragma unroll 1
+        for (int f = 0; f < 24; ++f)
+        {
+            double t = kHugeDouble;
+            const double4 pl = load_plane(planes + f);
+            const double dot = (pl.x * p.alpha + pl.y * p.beta + pl.z * p.gamma);
+            if (dot > 0.0)
+                t = distance_to_segment(plane_tolerance, dot, pl, nodes + 3 * c_facet_points[f][0],
+                                        nodes + 3 * c_facet_points[f][1], nodes + 3 * c_facet_points[f][2], p);
+            // MCT_Nearest_Facet_Find_Nearest folded into the loop: same order, same comparisons
+            if (t > 0.0) { if (t <= nf_distance) { nf_distance = t; nf_facet = f; } }
+            else if (t > neg_distance) { neg_distance = t; neg_facet = f; }
+        }
+        if (nf_distance == kHugeDouble && neg_distance != -kHugeDouble) { nf_distance = neg_distance; nf_facet = neg_facet; }
+
+        bool retry = false;
+        if ((nf_distance == kHugeDouble && move_factor > 0) || (p.nseg > 10000000 && nf_distance <= 0.0))
+        {
+            double mx = 0, my = 0, mz = 0;
+            for (int k = 0; k < 14; ++k) { mx += __ldg(nodes + 3 * k); my += __ldg(nodes + 3 * k + 1); mz += __ldg(nodes + 3 * k + 2); }
+            const double inv = 1.0 / ((double)14);
+            mx *= inv; my *= inv; mz *= inv;
+            p.x += move_factor * (mx - p.x);
+            p.y += move_factor * (my - p.y);
+            p.z += move_factor * (mz - p.z);
+            iteration++;
+            move_factor *= 2.0;
+            if (move_factor > 1.0e-2) move_factor = 1.0e-2;
+            retry = iteration != 10000;
+        }
+        if (!retry) break;
+    }
+    if (nf_distance < 0) nf_distance = 0;
+    out_facet = nf_facet; out_distance = nf_distance;
+}
+
+// ---- segment outcome: 0 collision, 1 facet crossing, 2 census -----------------------------------------
+__device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p)
+{
+    const DevImage& im = a.im;
+    const double particle_speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+
+    bool force_collision = false;
+    if (p.nmfp < 0.0) { force_collision = true; p.nmfp = kSmallDouble; }
+
+    const int mat = __ldg(im.cell_material + p.cell);
+    const double xs = __ldg(im.xs_total + (size_t)mat * im.n_groups + p.group);
+    p.total_xs = xs;
+    const double mean_free_path = (xs == 0.0) ? kHugeDouble : 1.0 / xs;
+
+    if (p.nmfp == 0.0)
+    {
+        const double r = qs_rng_sample(&p.seed);
+        p.nmfp = -1.0 * m_log(r);
+    }
+
+    double d_collision = force_collision ? kSmallDouble : p.nmfp * mean_free_path;
+    double d_census = particle_speed * p.ttc;
+    int nf_facet; double d_facet;
+    nearest_facet(im, p, nf_facet, d_facet);
+    if (force_collision) { d_facet = kHugeDouble; d_census = kHugeDouble; d_collision = kTinyDouble; }
+
+    // MC_Find_Min: strict <, ties to the lower index
+    int outcome = 0; double dmin = d_collision;
+    if (d_facet < dmin) { dmin = d_facet; outcome = 1; }
+    if (d_census < dmin) { dmin = d_census; outcome = 2; }
+
+    const double segment_path_length = dmin;
+    p.nmfp -= segment_path_length / mean_free_path;
+    p.last_event = outcome == 0 ? QSB_EV_COLLISION : (outcome == 1 ? QSB_EV_FACET_TRANSIT : QSB_EV_CENSUS);
+    if (outcome == 0) p.nmfp = 0.0;
+    else if (outcome == 1) p.facet = nf_facet;
+    else p.ttc = (p.ttc < 0.0) ? p.ttc : 0.0;
+    if (force_collision) p.nmfp = 0.0;
+
+    if (segment_path_length == 0.0) return outcome;
+
+    p.x += (p.alpha * segment_path_length);
+    p.y += (p.beta * segment_path_length);
+    p.z += (p.gamma * segment_path_length);
+    const double segment_path_time = (segment_path_length / particle_speed);
+    p.ttc -= segment_path_time;
+    p.age += segment_path_time;
+    if (p.ttc < 0.0) p.ttc = 0.0;
+
+    // scalar flux tally (src/Tallies.hh:351-354): fire-and-forget f64 reduction in L2
+    atomicAdd(a.flux + (size_t)p.cell * im.n_groups + p.group, segment_path_length * p.weight);
+    return outcome;
+}
+
+// ---- collision ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void update_trajectory(double energy, double angle, Particle& p)
+{
+    p.energy = energy;
+    const double cosTheta = angle;
+    double r = qs_rng_sample(&p.seed);
+    const double phi = 2 * 3.14159265 * r;
+    double sinPhi, cosPhi;
+    m_sincos(phi, &sinPhi, &cosPhi);
+    const double sinTheta = sqrt((1.0 - (cosTheta * cosTheta)));
+
+    const double cos_theta = p.gamma;
+    const double sin_theta = sqrt((1.0 - (cos_theta * cos_theta)));
+    double cos_phi, sin_phi;
+    if (sin_theta < 1e-6) { cos_phi = 1.0; sin_phi = 0.0; }
+    else { cos_phi = p.alpha / sin_theta; sin_phi = p.beta / sin_theta; }
+    const double na =  cos_theta * cos_phi * (sinTheta * cosPhi) - sin_phi * (sinTheta * sinPhi) + sin_theta * cos_phi * cosTheta;
+    const double nb =  cos_theta * sin_phi * (sinTheta * cosPhi) + cos_phi * (sinTheta * sinPhi) + sin_theta * sin_phi * cosTheta;
+    const double ng = -sin_theta           * (sinTheta * cosPhi) +                                 cos_theta           * cosTheta;
+    p.alpha = na; p.beta = nb; p.gamma = ng;
+
+    const double speed = (kSpeedOfLight *
+                          sqrt((1.0 - ((kNeutronRestMassEnergy * kNeutronRestMassEnergy) /
+                                       ((energy + kNeutronRestMassEnergy) * (energy + kNeutronRestMassEnergy))))));
+    p.vx = speed * p.alpha; p.vy = speed * p.beta; p.vz = speed * p.gamma;
+    r = qs_rng_sample(&p.seed);
+    p.nmfp = -1.0 * m_log(r);
+}
+
+// append a secondary to the processing vault; it becomes claimable once its ready word carries the epoch
+__device__ __forceinline__ void push_secondary(const TrackArgs& a, const Particle& child)
+{
+    const unsigned long long slot = atomicAdd(&a.ctl->tail, 1ull);
+    if (slot >= a.proc.capacity) { atomicOr(&a.ctl->overflow, 1u); return; }
+    store_particle(a.proc, slot, child, false);
+    __threadfence();
+    *((volatile uint32_t*)(a.proc.ready + slot)) = a.ctl->epoch;
+}
+
+// returns true when the particle keeps tracking
+__device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p, Counters& c)
+{
+    const DevImage& im = a.im;
+    const int mat = __ldg(im.cell_material + p.cell);
+    const double* __restrict__ table = im.xs_react + ((size_t)mat * im.n_groups + p.group) * im.max_react;
+    const int n_react_total = __ldg(im.mat_n_iso + mat) * __ldg(im.mat_n_react + mat);
+
+    double r = qs_rng_sample(&p.seed);
+    double current = p.total_xs * r;
+    // the reference's nested isotope/reaction loop visits the table in storage order and leaves both
+    // loops at the first negative running value (src/CollisionEvent.cc:67-83)
+    int selected = -1;
+    for (int k = 0; k < n_react_total; ++k)
+    {
+        current -= __ldg(table + k);
+        if (current < 0) { selected = k; break; }
+    }
+    c.lookups += (selected < 0 ? n_react_total : selected + 1);
+    if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return false; }
+
+    double energyOut[4], angleOut[4];
+    int nOut = 0;
+    const int rtype = __ldg(im.mat_react_type + (size_t)mat * im.max_react + selected);
+    if (rtype == QSB_REACT_SCATTER)
+    {
+        nOut = 1;
+        r = qs_rng_sample(&p.seed);
+        energyOut[0] = p.energy * (1.0 - (r * (1.0 / __ldg(im.mat_mass + mat))));
+        r = qs_rng_sample(&p.seed) * 2.0 - 1.0;
+        angleOut[0] = r;
+    }
+    else if (rtype == QSB_REACT_FISSION)
+    {
+        int n = (int)(__ldg(im.mat_nu_bar + mat) + qs_rng_sample(&p.seed));
+        if (n > 4) n = 4;
+        nOut = n;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            if (i < n)
+            {
+                r = qs_rng_sample(&p.seed) / 2.0 + 0.5;
+                energyOut[i] = (20 * r * r);
+                r = qs_rng_sample(&p.seed) * 2.0 - 1.0;
+                angleOut[i] = r;
+            }
+        }
+    }
+
+    c.collisions++;
+    if (rtype == QSB_REACT_SCATTER) c.scatters++;
+    else if (rtype == QSB_REACT_ABSORPTION) c.absorbs++;
+    else if (rtype == QSB_REACT_FISSION) { c.fissions++; c.produced += nOut; }
+
+    if (nOut == 0) return false;
+
+#pragma unroll
+    for (int s = 1; s < 4; ++s)
+    {
+        if (s < nOut)
+        {
+            Particle child = p;
+            child.seed = qs_rng_spawn(&p.seed);
+            child.id = child.seed;
+            update_trajectory(energyOut[s], angleOut[s], child);
+            push_secondary(a, child);
+        }
+    }
+    update_trajectory(energyOut[0], angleOut[0], p);
+    if (nOut > 1)
+    {
+        // the reference re-queues the fissioning parent as a base particle and loads it again later:
+        // direction cosine re-derived from the velocity, census clock / age fixed up
+        reload_transform(im, p, a.dt, true);
+        return true;
+    }
+    p.group = energy_group(im, p.energy);
+    return true;
+}
+
+// ---- facet crossing --------------------------------------------------------------------------------------
+__device__ __forceinline__ void reflect_particle(const DevImage& im, Particle& p)
+{
+    const double4 pl = load_plane(im.planes + (size_t)p.cell * 24 + p.facet);
+    const double dot = 2.0 * (p.alpha * pl.x + p.beta * pl.y + p.gamma * pl.z);
+    if (dot > 0)
+    {
+        p.alpha -= dot * pl.x;
+        p.beta  -= dot * pl.y;
+        p.gamma -= dot * pl.z;
+    }
+    const double speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+    p.vx = speed * p.alpha; p.vy = speed * p.beta; p.vz = speed * p.gamma;
+}
+
+__device__ __forceinline__ int flat_to_domain(const DevImage& im, int flat)
+{
+    int d = 0;
+    while (d + 1 < im.n_domains && flat >= __ldg(im.domain_cell_offset + d + 1)) d++;
+    return d;
+}
+
+__device__ __forceinline__ void fill_base(const DevImage& im, const Particle& p, qsb_base_particle& b)
+{
+    b.coordinate[0] = p.x; b.coordinate[1] = p.y; b.coordinate[2] = p.z;
+    b.velocity[0] = p.vx; b.velocity[1] = p.vy; b.velocity[2] = p.vz;
+    b.kinetic_energy = p.energy; b.weight = p.weight; b.time_to_census = p.ttc; b.age = p.age;
+    b.num_mean_free_paths = p.nmfp; b.num_segments = p.nseg;
+    b.random_number_seed = p.seed; b.identifier = p.id;
+    b.last_event = p.last_event; b.num_collisions = p.num_collisions; b.breed = p.breed; b.species = p.species;
+    const int d = flat_to_domain(im, p.cell);
+    b.domain = d; b.cell = p.cell - __ldg(im.domain_cell_offset + d);
+}
+
+// returns true when the particle keeps tracking
+__device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particle& p, Counters& c)
+{
+    const DevImage& im = a.im;
+    const size_t k = (size_t)p.cell * 6 + (p.facet >> 2);
+    const int event = __ldg(im.face_event + k);
+    if (event == QSB_ADJ_TRANSIT_ON)
+    {
+        p.cell = __ldg(im.face_adj_cell + k);
+        p.facet = c_opposing_facet[p.facet];
+        p.last_event = QSB_EV_FACET_TRANSIT;
+        return true;
+    }
+    if (event == QSB_ADJ_ESCAPE)
+    {
+        p.last_event = QSB_EV_ESCAPE;
+        p.species = -1;
+        c.escapes++;
+        return false;
+    }
+    if (event == QSB_ADJ_REFLECT)
+    {
+        p.last_event = QSB_EV_REFLECTION;
+        reflect_particle(im, p);
+        return true;
+    }
+    if (event == QSB_ADJ_TRANSIT_OFF)
+    {
+        p.last_event = QSB_EV_COMMUNICATION;
+        const int rank = __ldg(im.face_nbr_rank + k);
+        const unsigned long long slot = atomicAdd(&a.ctl->send_count[rank], 1ull);
+        if (slot >= a.send_capacity) { atomicOr(&a.ctl->overflow, 4u); return false; }
+        ExchangeRecord rec;
+        fill_base(im, p, rec.p);
+        rec.p.domain = __ldg(im.face_adj_domain + k);
+        rec.p.cell = __ldg(im.face_adj_cell + k);
+        rec.dir[0] = p.alpha; rec.dir[1] = p.beta; rec.dir[2] = p.gamma;
+        a.sends[(size_t)rank * a.send_capacity + slot] = rec;
+        return false;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void census_event(const TrackArgs& a, const Particle& p, Counters& c)
+{
+    const unsigned long long slot = atomicAdd(&a.ctl->census_count, 1ull);
+    c.census++;
+    if (slot >= a.census.capacity) { atomicOr(&a.ctl->overflow, 2u); return; }
+    store_particle(a.census, slot, p, false);
+}
+
+__device__ __forceinline__ unsigned int warp_sum(unsigned int v) { return __reduce_add_sync(kFullMask, v); }
+
+// ---- the persistent history kernel ---------------------------------------------------------------------
+template <int kDummy>
+__global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ TrackArgs a)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    Particle p;
+    bool have = false;
+    const uint32_t epoch = a.ctl->epoch;
+
+    for (;;)
+    {
+        __syncwarp();
+        const unsigned need = __ballot_sync(kFullMask, !have);
+        if (need)
+        {
+            // warp-aggregated claim of up to popc(need) consecutive slots; never past the allocated tail
+            unsigned long long base = 0; int got = 0;
+            if (lane == 0)
+            {
+                const int want = __popc(need);
+                unsigned long long h = *((volatile unsigned long long*)&a.ctl->head);
+                for (;;)
+                {
+                    unsigned long long t = *((volatile unsigned long long*)&a.ctl->tail);
+                    if (t > a.proc.capacity) t = a.proc.capacity;
+                    if (h >= t) { got = 0; break; }
+                    const unsigned long long n = (t - h < (unsigned long long)want) ? (t - h) : (unsigned long long)want;
+                    const unsigned long long old = atomicCAS(&a.ctl->head, h, h + n);
+                    if (old == h) { base = h; got = (int)n; break; }
+                    h = old;
+                }
+            }
+            base = __shfl_sync(kFullMask, base, 0);
+            got = __shfl_sync(kFullMask, got, 0);
+            if (!have)
+            {
+                const int rank = __popc(need & ((1u << lane) - 1u));
+                if (rank < got)
+                {
+                    const unsigned long long idx = base + rank;
+                    if (idx >= a.ready_prefix)
+                        while (*((volatile uint32_t*)(a.proc.ready + idx)) != epoch) { __nanosleep(64); }
+                    __threadfence();
+                    load_particle(a, idx, p);
+                    have = true;
+                }
+            }
+            if (__ballot_sync(kFullMask, have) == 0u) break;     // vault drained (for now): the host re-launches if secondaries remain
+        }
+
+        if (have)
+        {
+            const int outcome = segment_outcome(a, p);
+            c.segments++;
+            p.nseg += 1.;
+            bool keep;
+            if (outcome == 0) keep = collision_event(a, p, c);
+            else if (outcome == 1) keep = facet_crossing_event(a, p, c);
+            else { census_event(a, p, c); keep = false; }
+            have = keep;
+        }
+    }
+
+    // flush the per-thread balance counters: warp sum, one atomic per counter per warp
+    __syncwarp();
+    const unsigned int s_seg = warp_sum(c.segments), s_col = warp_sum(c.collisions), s_sca = warp_sum(c.scatters);
+    const unsigned int s_abs = warp_sum(c.absorbs), s_fis = warp_sum(c.fissions), s_pro = warp_sum(c.produced);
+    const unsigned int s_esc = warp_sum(c.escapes), s_cen = warp_sum(c.census), s_look = warp_sum(c.lookups);
+    if (lane == 0)
+    {
+        unsigned long long* b = a.ctl->balance;
+        if (s_seg) atomicAdd(b + QSB_BAL_NUM_SEGMENTS, (unsigned long long)s_seg);
+        if (s_col) atomicAdd(b + QSB_BAL_COLLISION, (unsigned long long)s_col);
+        if (s_sca) atomicAdd(b + QSB_BAL_SCATTER, (unsigned long long)s_sca);
+        if (s_abs) atomicAdd(b + QSB_BAL_ABSORB, (unsigned long long)s_abs);
+        if (s_fis) atomicAdd(b + QSB_BAL_FISSION, (unsigned long long)s_fis);
+        if (s_pro) atomicAdd(b + QSB_BAL_PRODUCE, (unsigned long long)s_pro);
+        if (s_esc) atomicAdd(b + QSB_BAL_ESCAPE, (unsigned long long)s_esc);
+        if (s_cen) atomicAdd(b + QSB_BAL_CENSUS, (unsigned long long)s_cen);
+        if (s_look) atomicAdd(&a.ctl->n_lookups, (unsigned long long)s_look);
+    }
+}
+
+} // namespace
+
+#if QSB_VALIDATION
+#define QSB_LAUNCH_NAME launch_track_validation
+#define QSB_ATTR_NAME track_kernel_attributes_validation
+#else
+#define QSB_LAUNCH_NAME launch_track_fast
+#define QSB_ATTR_NAME track_kernel_attributes_fast
+#endif
+
+void QSB_LAUNCH_NAME(const TrackArgs& a, int grid, int block, cudaStream_t s)
+{
+    track_kernel<QSB_VALIDATION><<<grid, block, 0, s>>>(a);
+}
+
+void QSB_ATTR_NAME(int* regs, int* max_blocks_per_sm, int block)
+{
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, track_kernel<QSB_VALIDATION>) == cudaSuccess && regs) *regs = attr.numRegs;
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, track_kernel<QSB_VALIDATION>, block, 0);
+    if (max_blocks_per_sm) *max_blocks_per_sm = nb;
+}
+
+} // namespace qsb

@@ -209,3 +209,26 @@ int qsb_mc_format_cycle_row(qsb_mc* h, int cycle, const uint64_t row[QSB_BAL_COU
 }
 
 } // extern "C"
+
+// Drop-in for the reference's cycleTracking(MonteCarlo*) (src/main.cc:138-307) on one rank, written
+// purely against the device C ABI: host vault in, census + tallies out, copies included.
+extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* stats)
+{
+    if (!ctx) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
+        int rc;
+        if ((rc = qsb_cycle_begin(ctx, 0)) != QSB_OK) return fail(rc);
+        if ((rc = qsb_put_particles(ctx, mc.processing.data(), mc.processing.size())) != QSB_OK) return fail(rc);
+        if ((rc = qsb_track(ctx, stats)) != QSB_OK) return fail(rc);
+        uint64_t n = 0;
+        if ((rc = qsb_census_count(ctx, &n)) != QSB_OK) return fail(rc);
+        h->scratch.resize(n);
+        if ((rc = qsb_get_census(ctx, h->scratch.data(), n, &n)) != QSB_OK) return fail(rc);
+        uint64_t bal[QSB_BAL_COUNT];
+        double flux = 0.0;
+        if ((rc = qsb_get_balance(ctx, bal)) != QSB_OK) return fail(rc);
+        if ((rc = qsb_scalar_flux_sum(ctx, &flux)) != QSB_OK) return fail(rc);
+        return qsb_mc_set_tracking_result(h, h->scratch.data(), n, bal, flux);
+    });
+}

@@ -1,0 +1,72 @@
+// qs_main.cc -- the `qs_b200` executable: the reference's command line, cycle loop and report
+// (src/main.cc:38-94) over the C ABI of libqsb.so, single GPU.  Multi-GPU runs are driven by
+// quicksilver_b200/driver.py (one process per GPU under torch.distributed).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../../include/qsb.h"
+
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int main(int argc, char** argv)
+{
+    qsb_mc* mc = nullptr;
+    if (qsb_mc_create(argc, argv, 0, 1, &mc) != QSB_OK)
+    {
+        std::fprintf(stderr, "%s\n", qsb_mc_last_error(nullptr));
+        return 2;
+    }
+    uint64_t need = 0;
+    qsb_mc_print_parameters(mc, nullptr, 0, &need);
+    std::vector<char> text(need);
+    qsb_mc_print_parameters(mc, text.data(), need, nullptr);
+    std::printf("%s", text.data());
+
+    qsb_image image;
+    qsb_mc_get_image(mc, &image);
+    int64_t n_steps = 0, n_particles = 0;
+    double dt = 0, nu_bar = 0;
+    qsb_mc_get_int(mc, "nSteps", &n_steps);
+    qsb_mc_get_int(mc, "nParticles", &n_particles);
+    qsb_mc_get_double(mc, "dt", &dt);
+    qsb_mc_get_double(mc, "max_nu_bar", &nu_bar);
+
+    qsb_options opt = {};
+    const char* fast = std::getenv("QSB_FAST");
+    opt.validation = (fast && fast[0] == '1') ? 0 : 1;
+    opt.particle_capacity = (uint64_t)(n_particles * 6 + 65536);
+    qsb_ctx* ctx = nullptr;
+    if (qsb_create(0, &image, dt, &opt, &ctx) != QSB_OK)
+    {
+        std::fprintf(stderr, "qsb_create: %s\n", qsb_last_error(nullptr));
+        return 3;
+    }
+
+    double t_track_total = 0;
+    for (int cycle = 0; cycle < n_steps; ++cycle)
+    {
+        const double t0 = now();
+        if (qsb_mc_cycle_init(mc) != QSB_OK) { std::fprintf(stderr, "%s\n", qsb_mc_last_error(mc)); return 4; }
+        const double t1 = now();
+        qsb_track_stats stats;
+        if (qsb_mc_cycle_tracking(mc, ctx, &stats) != QSB_OK) { std::fprintf(stderr, "%s\n", qsb_mc_last_error(mc)); return 5; }
+        const double t2 = now();
+        uint64_t row[QSB_BAL_COUNT]; double flux = 0;
+        qsb_mc_cycle_finalize(mc, row, &flux);
+        const double t3 = now();
+        char line[2048];
+        qsb_mc_format_cycle_row(mc, cycle, row, flux, t1 - t0, t2 - t1, t3 - t2, line, sizeof line);
+        std::printf("%s", line);
+        t_track_total += t2 - t1;
+    }
+    uint64_t cum[QSB_BAL_COUNT];
+    qsb_mc_cumulative_balance(mc, cum);
+    // src/MC_Fast_Timer.cc:97-104
+    std::printf("%-25s %12.3e %-25s\n", "Figure Of Merit", cum[QSB_BAL_NUM_SEGMENTS] / t_track_total, "[Num Segments / Cycle Tracking Time]");
+    qsb_destroy(ctx);
+    qsb_mc_destroy(mc);
+    return 0;
+}

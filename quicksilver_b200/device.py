@@ -1,0 +1,96 @@
+"""Device context wrapper (qsb_ctx): one GPU's flattened problem image, SoA vaults and the sm_100a
+tracking kernels behind the C ABI of include/qsb.h.  No CPU fallback: creation fails with QsbError
+(QSB_ERR_CUDA) when no B200-class device is usable."""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE, QsbError
+
+
+class DeviceContext:
+    def __init__(self, image, dt, device=0, validation=True, particle_capacity=0, send_capacity=0,
+                 threads_per_block=0, blocks_per_sm=0):
+        self._lib = _capi.lib()
+        self.image = image
+        self.opt = _capi.Options(int(bool(validation)), 0, int(particle_capacity), int(send_capacity),
+                                 int(threads_per_block), int(blocks_per_sm))
+        self._h = C.c_void_p()
+        rc = self._lib.qsb_create(int(device), C.byref(image), float(dt), C.byref(self.opt), C.byref(self._h))
+        if rc != 0:
+            raise QsbError(rc, (self._lib.qsb_last_error(None) or b"").decode())
+        self.n_ranks = image.n_ranks
+
+    def _check(self, rc):
+        if rc != 0:
+            raise QsbError(rc, (self._lib.qsb_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qsb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cycle_begin(self, keep_census=False):
+        self._check(self._lib.qsb_cycle_begin(self._h, int(keep_census)))
+
+    def put_particles(self, particles):
+        p = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        self._check(self._lib.qsb_put_particles(self._h, p.ctypes.data_as(C.c_void_p), len(p)))
+
+    def track(self):
+        stats = _capi.TrackStats()
+        self._check(self._lib.qsb_track(self._h, C.byref(stats)))
+        return stats
+
+    def census_count(self):
+        n = C.c_uint64()
+        self._check(self._lib.qsb_census_count(self._h, C.byref(n)))
+        return n.value
+
+    def get_census(self):
+        n = self.census_count()
+        out = np.zeros(n, dtype=PARTICLE_DTYPE)
+        got = C.c_uint64()
+        self._check(self._lib.qsb_get_census(self._h, out.ctypes.data_as(C.c_void_p), n, C.byref(got)))
+        return out[:got.value]
+
+    def get_balance(self):
+        out = np.zeros(BAL_COUNT, dtype=np.uint64)
+        self._check(self._lib.qsb_get_balance(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def get_scalar_flux(self):
+        out = np.zeros((self.image.n_cells, self.image.n_groups))
+        self._check(self._lib.qsb_get_scalar_flux(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def scalar_flux_sum(self):
+        s = C.c_double()
+        self._check(self._lib.qsb_scalar_flux_sum(self._h, C.byref(s)))
+        return s.value
+
+    def send_counts(self):
+        out = np.zeros(self.n_ranks, dtype=np.uint64)
+        self._check(self._lib.qsb_send_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def send_slab(self, peer):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.qsb_send_slab(self._h, int(peer), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def clear_sends(self):
+        self._check(self._lib.qsb_clear_sends(self._h))
+
+    def put_arrivals(self, device_ptr, n):
+        self._check(self._lib.qsb_put_arrivals(self._h, C.c_void_p(device_ptr), int(n)))
+
+    def launch_count(self):
+        return int(self._lib.qsb_launch_count(self._h))

@@ -1,0 +1,265 @@
+"""Cycle driver: the reference's main loop (src/main.cc:38-121,138-324) for one process per GPU.
+
+Single GPU: cycle_init (host) -> qsb_mc_cycle_tracking (device) -> cycle_finalize (host).
+Several GPUs: the spatial domain decomposition gives each rank one domain; boundary-crossing particles
+leave the tracking kernel in per-peer slabs and are exchanged between ranks with torch.distributed
+(NCCL send/recv over NVLink for device slabs, gloo for the CPU protocol tests); termination is the
+reference's "gains == losses" test reduced to "nobody sent anything this round"
+(src/MC_Particle_Buffer.cc:601-618).  torch is plumbing only: device memory views and collectives.
+"""
+import time
+
+import numpy as np
+
+from . import _capi, device as device_mod, host as host_mod
+from ._capi import BAL, BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE
+
+RECORD_BYTES = EXCHANGE_DTYPE.itemsize
+
+
+class _DeviceMemory:
+    """__cuda_array_interface__ shim so torch can view a slab owned by the qsb_ctx without copying."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class DeviceBackend:
+    """tracking backend over a qsb_ctx (the product path)."""
+
+    def __init__(self, ctx, torch_device):
+        self.ctx, self.torch_device = ctx, torch_device
+
+    def begin(self, vault):
+        self.ctx.cycle_begin()
+        self.ctx.put_particles(vault)
+
+    def track(self):
+        return self.ctx.track()
+
+    def send_counts(self):
+        return self.ctx.send_counts().astype(np.int64)
+
+    def send_tensor(self, peer, n):
+        import torch
+        ptr, have = self.ctx.send_slab(peer)
+        assert have == n
+        return torch.as_tensor(_DeviceMemory(ptr, n * RECORD_BYTES), device=self.torch_device)
+
+    def recv_tensor(self, n):
+        import torch
+        return torch.empty(n * RECORD_BYTES, dtype=torch.uint8, device=self.torch_device)
+
+    def put_arrivals(self, tensor, n):
+        import torch
+        torch.cuda.synchronize(self.torch_device)
+        self.ctx.put_arrivals(tensor.data_ptr(), n)
+
+    def clear_sends(self):
+        self.ctx.clear_sends()
+
+    def results(self):
+        return self.ctx.get_census(), self.ctx.get_balance(), self.ctx.scalar_flux_sum()
+
+
+def exchange_rounds(backend, dist, rank, world, max_rounds=100000):
+    """Track to exhaustion, swap boundary particles, repeat until no rank sent anything.
+    Returns (rounds, records sent by this rank)."""
+    import torch
+    sent_total, rounds = 0, 0
+    while True:
+        backend.track()
+        rounds += 1
+        if world == 1:
+            return rounds, 0
+        counts = backend.send_counts()
+        counts[rank] = 0
+        is_cuda = dist.get_backend() == "nccl"
+        dev = backend.torch_device if is_cuda else "cpu"
+        send_counts = torch.as_tensor(counts, dtype=torch.int64, device=dev)
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts)
+        total = send_counts.sum().reshape(1).clone()
+        dist.all_reduce(total)
+        recv = recv_counts.cpu().numpy()
+        if int(total.item()) == 0:
+            return rounds, sent_total
+        n_in = int(recv.sum())
+        inbox = backend.recv_tensor(n_in)
+        ops, offset, keep = [], 0, []
+        for peer in range(world):
+            if peer == rank:
+                continue
+            if recv[peer]:
+                nbytes = int(recv[peer]) * RECORD_BYTES
+                ops.append(dist.P2POp(dist.irecv, inbox[offset:offset + nbytes], peer))
+                offset += nbytes
+            if counts[peer]:
+                t = backend.send_tensor(peer, int(counts[peer]))
+                keep.append(t)
+                ops.append(dist.P2POp(dist.isend, t, peer))
+        if ops:
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+        sent_total += int(counts.sum())
+        backend.clear_sends()
+        if n_in:
+            backend.put_arrivals(inbox, n_in)
+        if rounds >= max_rounds:
+            raise RuntimeError("particle exchange did not terminate")
+
+
+class Simulation:
+    """One rank of a run: host model + device context + the cycle loop."""
+
+    def __init__(self, argv, rank=0, world=1, device=0, validation=True, dist=None, particle_capacity=0, send_capacity=0):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.torch_device = "cuda:%d" % device
+        self.mc = host_mod.MonteCarlo(argv, rank, world, allreduce=self._allreduce if world > 1 else None)
+        n_particles = self.mc.get_int("nParticles")
+        if particle_capacity == 0:
+            per_rank = (n_particles + world - 1) // world
+            particle_capacity = int(per_rank * (3 + 2 * self.mc.get_double("max_nu_bar"))) + (1 << 16)
+        self.ctx = device_mod.DeviceContext(self.mc.image, self.mc.get_double("dt"), device=device, validation=validation,
+                                            particle_capacity=particle_capacity, send_capacity=send_capacity)
+        self.backend = DeviceBackend(self.ctx, self.torch_device)
+
+    def _allreduce(self, arr):
+        import torch
+        is_cuda = self.dist.get_backend() == "nccl"
+        view = arr.view(np.int64) if arr.dtype == np.uint64 else arr
+        t = torch.from_numpy(view.copy())
+        if is_cuda:
+            t = t.to(self.torch_device)
+        self.dist.all_reduce(t)
+        view[:] = t.cpu().numpy()
+
+    def cycle(self):
+        """one cycle; returns (global balance row, global flux sum, timings dict)."""
+        t0 = time.perf_counter()
+        self.mc.cycle_init()
+        t1 = time.perf_counter()
+        info = {}
+        if self.world == 1:
+            stats = self.mc.cycle_tracking(self.ctx)
+            info.update(device_ms=stats.device_ms, launches=stats.n_launches, rounds=1)
+        else:
+            vault = self.mc.processing()
+            self.backend.begin(vault)
+            rounds, sent = exchange_rounds(self.backend, self.dist, self.rank, self.world)
+            census, balance, flux_sum = self.backend.results()
+            self.mc.set_tracking_result(census, balance, flux_sum)
+            info.update(rounds=rounds, sent=sent)
+        t2 = time.perf_counter()
+        row, flux = self.mc.cycle_finalize()
+        t3 = time.perf_counter()
+        info.update(t_init=t1 - t0, t_track=t2 - t1, t_final=t3 - t2)
+        return row, flux, info
+
+    def close(self):
+        self.ctx.close()
+        self.mc.close()
+
+
+def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder, deck_argv, ClockSampler):
+    """bench.py's B200 arm.  Times, per step, (a) the device-resident tracking (CUDA events inside qsb_track)
+    and (b) the host-buffer drop-in call, and returns totals reduced over ranks (max of times, sum of segments)."""
+    import tempfile
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = "cuda:%d" % local_rank
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    w = dict(workloads[args.workload])
+    if args.scale != 1.0:
+        k = args.scale ** (1.0 / 3.0)
+        w["n"] = max(4, int(round(w["n"] * k)))
+        w["particles"] = int(w["particles"] * (w["n"] / workloads[args.workload]["n"]) ** 3)
+    grid = grid_ladder[world]
+    tmp = tempfile.mkdtemp(prefix="qsb_bench_")
+    argv = deck_argv(w, grid, tmp, warmup + args.steps)
+
+    sim = Simulation(argv, rank, world, device=local_rank, validation=not args.fast, dist=dist if world > 1 else None)
+    mc, ctx = sim.mc, sim.ctx
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    kernel_s = e2e_s = 0.0
+    segments = 0
+    h2d = d2h = 0
+    launches0 = 0
+    rows = []
+    sampler = ClockSampler(local_rank)
+    for step in range(warmup + args.steps):
+        timed = step >= warmup
+        if step == warmup:
+            barrier()
+            sampler.start()
+            launches0 = ctx.launch_count()
+        mc.cycle_init()
+        n_in = mc.get_int("nProcessing")
+        if world == 1:
+            # (b) host buffers in, host buffers out: wall clock around the drop-in call
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            stats = mc.cycle_tracking(ctx)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            step_kernel_s, step_e2e_s = stats.device_ms * 1e-3, t1 - t0
+            n_census = stats.n_census
+        else:
+            vault = mc.processing()
+            barrier()
+            t0 = time.perf_counter()
+            sim.backend.begin(vault)
+            ta = time.perf_counter()
+            exchange_rounds(sim.backend, dist, rank, world)
+            torch.cuda.synchronize()
+            tb = time.perf_counter()
+            census, balance, flux_sum = sim.backend.results()
+            mc.set_tracking_result(census, balance, flux_sum)
+            t1 = time.perf_counter()
+            step_kernel_s, step_e2e_s = tb - ta, t1 - t0
+            n_census = len(census)
+        row, flux = mc.cycle_finalize()     # global row (allreduced)
+        rows.append([int(v) for v in row])
+        if timed:
+            kernel_s += step_kernel_s
+            e2e_s += step_e2e_s
+            segments += int(row[BAL["num_segments"]])
+            h2d += n_in * PARTICLE_DTYPE.itemsize
+            d2h += n_census * PARTICLE_DTYPE.itemsize + BAL_COUNT * 8 + 8
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+
+    # reduce over ranks: max of times, segments already global
+    times = torch.tensor([kernel_s, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    kernel_max, e2e_max = (float(v) for v in times.cpu())
+    # conservation identity of the reference's MissingParticleTest (src/CoralBenchmark.cc:152-174)
+    cum = mc.cumulative_balance()
+    gains = int(cum[BAL["start"]] + cum[BAL["source"]] + cum[BAL["produce"]] + cum[BAL["split"]])
+    losses = int(cum[BAL["absorb"]] + cum[BAL["census"]] + cum[BAL["escape"]] + cum[BAL["rr"]] + cum[BAL["fission"]])
+    n = w["n"]
+    config = {"workload": "%s weak-scaled: %dx%dx%d cells and %d particles per GPU, %s domain grid" % (
+                  args.workload, n, n, n, w["particles"], "x".join(str(g) for g in grid)),
+              "deck": w["deck"], "cells_per_gpu": n ** 3, "particles_per_gpu": w["particles"], "domain_grid": list(grid),
+              "kernels": "fast" if args.fast else "validation", "timing": "inputs larger than L2 (vault %.0f MB, mesh %.0f MB per GPU)" % (
+                  w["particles"] * 160 / 1e6, n ** 3 * 1.2e-3), "scale": args.scale}
+    out = {"segments_total": segments, "kernel_seconds_max": kernel_max, "e2e_seconds_max": e2e_max,
+           "segments_rank0": segments / world, "kernel_seconds_rank0": kernel_s, "config": config, "clocks": clocks,
+           "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
+           "gpu_launches": launches, "traffic": None,
+           "balance_check": {"gains": gains, "losses": losses, "conserved": gains == losses, "last_row": rows[-1]}}
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return out

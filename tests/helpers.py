@@ -110,3 +110,11 @@ def oracle_track(image, dt, particles, arrivals=None, strict=False, threads=1, c
 
 def sort_particles(p):
     return p[np.argsort(p["identifier"], kind="stable")]
+
+
+def golden_table(name):
+    """rows of the reference's cycle table captured in BASELINE.md section 4: [(12 ints, flux), ...];
+    columns start source rr split absorb scatter fission produce collisn escape census num_seg."""
+    import json
+    with open(os.path.join(GOLDEN, "balance_tables.json")) as f:
+        return [(r[0], r[1]) for r in json.load(f)[name]["rows"]]
