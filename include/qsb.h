@@ -170,7 +170,8 @@ typedef struct qsb_ctx qsb_ctx;
 typedef struct qsb_options {
     int32_t  validation;        /* 1: --fmad=false kernels + strict log/sin/cos (bit-exact vs oracle);
                                    0: fast build (FMA contraction, CUDA libm)                          */
-    int32_t  tracking_mode;     /* 0: history-based persistent kernel (default)                         */
+    int32_t  tracking_mode;     /* bit 0 reserved (0: history-based persistent kernel); bit 1 (value 2): run the
+                                   filtered and the full nearest-facet search side by side and count mismatches  */
     uint64_t particle_capacity; /* SoA slots per vault; 0 = derive from nParticles and nuBar            */
     uint64_t send_capacity;     /* slots per peer send/recv slab; 0 = derive                             */
     int32_t  threads_per_block; /* 0 = default                                                           */
@@ -208,6 +209,10 @@ int  qsb_clear_sends(qsb_ctx* ctx);
 int  qsb_put_arrivals(qsb_ctx* ctx, const void* device_records, uint64_t n_records);
 uint64_t qsb_exchange_record_bytes(void);
 const char* qsb_last_error(qsb_ctx* ctx);
+/* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] fast/full geometry
+ * disagreements (check mode; must be 0), [2] reaction-table entries scanned, [3] compact geometry enabled,
+ * [4] registers per thread, [5] resident blocks per SM, [6] grid size, [7] vault slots used. */
+int  qsb_get_diagnostics(qsb_ctx* ctx, uint64_t out[8]);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t qsb_launch_count(qsb_ctx* ctx);
 

@@ -126,6 +126,7 @@ def _declare(lib):
         "qsb_exchange_record_bytes": (C.c_uint64, []),
         "qsb_last_error": (C.c_char_p, [vp]),
         "qsb_launch_count": (C.c_uint64, [vp]),
+        "qsb_get_diagnostics": (C.c_int, [vp, u64p]),
         "qsb_mc_cycle_tracking": (C.c_int, [vp, vp, _P(TrackStats)]),
     }
     missing = []

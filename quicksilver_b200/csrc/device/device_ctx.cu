@@ -163,6 +163,8 @@ struct qsb_ctx
     double dt = 0;
     unsigned long long host_tail = 0;   // slots written from the host side this cycle
     unsigned long long ready_prefix = 0;
+    unsigned long long consumed = 0;         // slots fully processed by earlier qsb_track calls of this cycle
+    unsigned long long pending_inflight = 0; // histories written from the host side since the last qsb_track
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
@@ -285,6 +287,63 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         im.mat_periodic = (const uint8_t*)place(image->mat_periodic, nm, b_periodic);
         QSB_CUDA(cudaMemcpy(hot, h.data(), hot_bytes, cudaMemcpyHostToDevice));
 
+        // ---- compact cell records + {total, 1/total} pairs ----
+        {
+            const int nx = image->global_nx, ny = image->global_ny;
+            im.dx = image->global_lx / image->global_nx;      // the host grid's own expressions (src/GlobalFccGrid.cc:26-28)
+            im.dy = image->global_ly / image->global_ny;
+            im.dz = image->global_lz / image->global_nz;
+            im.margin = 1e-6 * std::min(im.dx, std::min(im.dy, im.dz));
+            im.inv_hx = 2.0 / im.dx; im.inv_hy = 2.0 / im.dy; im.inv_hz = 2.0 / im.dz;
+            std::vector<CellRec> recs(nc);
+            bool compact = image->global_nx < 65535 && image->global_ny < 65535 && image->global_nz < 65535 && nm <= 255;
+            const double cell_size[3] = { im.dx, im.dy, im.dz };
+            for (size_t cidx = 0; cidx < nc; ++cidx)
+            {
+                CellRec& r = recs[cidx];
+                std::memset(&r, 0, sizeof(r));
+                const int gid = image->cell_gid[cidx];
+                const int ijk[3] = { gid % nx, (gid / nx) % ny, gid / (nx * ny) };
+                r.ix = (uint16_t)ijk[0]; r.iy = (uint16_t)ijk[1]; r.iz = (uint16_t)ijk[2];
+                r.material = (uint8_t)image->cell_material[cidx];
+                for (int face = 0; face < 6; ++face)
+                {
+                    r.events |= (uint32_t)(image->face_event[cidx * 6 + face] & 0xf) << (4 * face);
+                    r.adj[face] = image->face_adj_cell[cidx * 6 + face];
+                }
+                // corner nodes must be index * cell size exactly (points 0 and 7 of the 14-point list)
+                const double* nodes = image->nodes + cidx * 42;
+                for (int ax = 0; ax < 3; ++ax)
+                    if (nodes[ax] != ijk[ax] * cell_size[ax] || nodes[21 + ax] != (ijk[ax] + 1) * cell_size[ax]) compact = false;
+                for (int f = 0; f < 24 && compact; ++f)
+                {
+                    const double* pl = image->planes + (cidx * 24 + f) * 4;
+                    const int face = f / 4, ax = face / 2;
+                    const double sign = (face & 1) ? -1.0 : 1.0;
+                    const double coord = (face & 1) ? ijk[ax] * cell_size[ax] : (ijk[ax] + 1) * cell_size[ax];
+                    unsigned code = 0;
+                    const double below_one = 0.99999999999999988897769753748;   // 1 - 2^-53
+                    if (pl[ax] == sign * 1.0) code = 0;
+                    else if (pl[ax] == sign * below_one) code = 1;
+                    else compact = false;
+                    for (int o = 0; o < 3; ++o) if (o != ax && pl[o] != 0.0) compact = false;
+                    long long cb, db;
+                    const double dabs = std::fabs(pl[3]);
+                    std::memcpy(&cb, &coord, 8); std::memcpy(&db, &dabs, 8);
+                    const long long k = db - cb;
+                    if (k == 0) code |= 0; else if (k == 1) code |= 2; else if (k == -1) code |= 4; else compact = false;
+                    // sign of D: -sign * |D| (either sign of zero is acceptable, the fast path never meets it)
+                    if (dabs != 0.0 && ((pl[3] < 0) != (sign > 0))) compact = false;
+                    r.code[f] = (uint8_t)code;
+                }
+            }
+            im.compact = compact ? 1 : 0;
+            im.cells = devUpload(recs.data(), nc, c->owned);
+            std::vector<double2> pairs(nm * ng);
+            for (size_t i = 0; i < nm * ng; ++i) { pairs[i].x = image->xs_total[i]; pairs[i].y = 1.0 / image->xs_total[i]; }
+            im.xs_pair = devUpload(pairs.data(), nm * ng, c->owned);
+        }
+
         // pin the hot block in L2 (126 MB on B200): persisting carve-out + access-policy window on our stream
         {
             size_t want = std::min<size_t>(hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
@@ -374,6 +433,8 @@ int qsb_cycle_begin(qsb_ctx* c, int keep_census)
         c->h_ctl->tail = carried;
         c->host_tail = carried;
         c->ready_prefix = carried;
+        c->consumed = 0;
+        c->pending_inflight = carried;
         pushControl(c);
         QSB_CUDA(cudaMemsetAsync(c->flux, 0, (size_t)c->im.n_cells * c->im.n_groups * sizeof(double), c->stream));
         c->in_cycle = true;
@@ -408,6 +469,7 @@ int qsb_put_particles(qsb_ctx* c, const qsb_base_particle* aos, uint64_t n)
         c->host_tail += n;
         c->ready_prefix = c->host_tail;
         c->h_ctl->tail = c->host_tail;
+        c->pending_inflight += n;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         return (int)QSB_OK;
     });
@@ -428,6 +490,7 @@ int qsb_put_arrivals(qsb_ctx* c, const void* device_records, uint64_t n)
         c->launches++;
         QSB_CUDA(cudaGetLastError());
         c->h_ctl->tail = first + n;
+        c->pending_inflight += n;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         QSB_CUDA(cudaStreamSynchronize(c->stream));
         return (int)QSB_OK;
@@ -444,26 +507,33 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.census = c->vault[1 - c->proc];
         a.sends = c->sends; a.send_capacity = c->send_capacity;
         a.ctl = c->d_ctl; a.flux = c->flux; a.dt = c->dt; a.ready_prefix = c->ready_prefix;
+        a.epoch = c->epoch; a.check_geometry = (c->opt.tracking_mode & 2) ? 1 : 0;
         uint32_t n_launch = 0;
+        // tickets handed out past the tail by the previous call were never redeemed: restart at the consumed mark
+        c->h_ctl->head = c->consumed;
+        c->h_ctl->inflight = c->pending_inflight;
+        c->pending_inflight = 0;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->head, &c->h_ctl->head, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->inflight, &c->h_ctl->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
-        for (;;)
+        if (c->h_ctl->inflight > 0)
         {
             if (c->opt.validation) launch_track_validation(a, c->grid, c->block, c->stream);
             else                   launch_track_fast(a, c->grid, c->block, c->stream);
             QSB_CUDA(cudaGetLastError());
             ++n_launch; c->launches++;
-            pullControl(c);
-            const unsigned long long tail = std::min<unsigned long long>(c->h_ctl->tail, a.proc.capacity);
-            if (c->h_ctl->head >= tail) break;     // every allocated slot has been consumed
-            if (n_launch > 100000) { c->error = "tracking did not converge"; return (int)QSB_ERR_INTERNAL; }
         }
         QSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        pullControl(c);
         QSB_CUDA(cudaEventSynchronize(c->ev1));
         float ms = 0;
         QSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (c->h_ctl->inflight != 0 && !c->h_ctl->overflow)
+        { c->error = "tracking kernel ended with histories in flight"; return (int)QSB_ERR_INTERNAL; }
+        c->consumed = std::min<unsigned long long>(c->h_ctl->tail, a.proc.capacity);
         if (stats)
         {
-            stats->n_processed = c->h_ctl->head;
+            stats->n_processed = c->consumed;
             stats->n_census = c->h_ctl->census_count;
             unsigned long long sent = 0;
             for (int r = 0; r < c->n_ranks; ++r) sent += c->h_ctl->send_count[r];
@@ -481,6 +551,18 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         }
         if (c->h_ctl->bad_reaction)
         { c->error = "a collision selected no reaction (cross-section table inconsistent)"; return (int)QSB_ERR_INTERNAL; }
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_get_diagnostics(qsb_ctx* c, uint64_t out[8])
+{
+    if (!out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        pullControl(c);
+        out[0] = c->h_ctl->slow_geometry; out[1] = c->h_ctl->geometry_mismatch; out[2] = c->h_ctl->n_lookups;
+        out[3] = (uint64_t)c->im.compact; out[4] = (uint64_t)c->regs; out[5] = (uint64_t)c->blocks_per_sm;
+        out[6] = (uint64_t)c->grid; out[7] = c->h_ctl->tail;
         return (int)QSB_OK;
     });
 }

@@ -8,10 +8,35 @@
 
 namespace qsb {
 
+// Compact per-cell record, 64 bytes (two sectors), everything the common tracking path reads about a cell.
+// The mesh is always a uniform brick grid (reference: GlobalFccGrid), so a cell's 24 facet planes are
+// axis aligned: the one non-zero normal component is +-1 or +-(1 - 2^-53) and D is the face coordinate
+// displaced by -1/0/+1 ulp (rounding of src/MC_Facet_Geometry.hh:18-39).  code[f] records exactly that:
+// bit0 = |normal| is 1 - 2^-53, bits1-2 = ulp displacement of |D| (0: none, 1: +1, 2: -1); the node
+// coordinates themselves are index * cell size, so the full-precision plane is rebuilt in registers.
+// The host verifies bit-for-bit that every facet decodes to the reference plane before enabling it.
+struct __align__(16) CellRec
+{
+    uint16_t ix, iy, iz;        // global cell indices
+    uint8_t  material;
+    uint8_t  flags;
+    uint32_t events;            // 4 bits per face: QSB_ADJ_*
+    uint32_t pad;
+    int32_t  adj[6];            // per face: adjacent flat cell (on-processor) / neighbour-domain cell (off-processor)
+    uint8_t  code[24];          // per facet, see above
+};
+static_assert(sizeof(CellRec) == 64, "CellRec layout");
+
 // read-only problem image in HBM (see include/qsb.h: qsb_image for the meaning of each array)
 struct DevImage
 {
     int n_cells, n_groups, n_materials, max_react, n_domains, n_ranks;
+    int compact;                    // 1: CellRec codes reproduce every plane bit-for-bit -> fast geometry path enabled
+    double dx, dy, dz;              // cell size (global_l / global_n, the host grid's own expression)
+    double margin;                  // robustness margin of the fast geometry path: 1e-6 * smallest cell edge
+    double inv_hx, inv_hy, inv_hz;  // 2/dx, 2/dy, 2/dz (filter arithmetic only)
+    const CellRec* cells;           // [n_cells]
+    const double2* xs_pair;         // [n_materials*n_groups] {total, 1/total}
     const double4* planes;          // [n_cells*24] {A,B,C,D}, 32-byte aligned records
     const double*  nodes;           // [n_cells*42]
     const int*     face_adj_cell;   // [n_cells*6]
@@ -59,6 +84,9 @@ struct DevControl
     unsigned long long head;            // next unclaimed slot of the processing vault
     unsigned long long tail;            // slots allocated (initial + arrivals + secondaries)
     unsigned long long census_count;
+    unsigned long long inflight;        // histories created and not yet finished (queued + running); 0 = cycle drained
+    unsigned long long slow_geometry;   // segments that took the full 24-facet path
+    unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];
     unsigned long long n_lookups;       // diagnostics
     unsigned int overflow;              // bit0 processing vault, bit1 census vault, bit2 send slab
@@ -79,6 +107,8 @@ struct TrackArgs
     double* flux;                       // [n_cells][n_groups]
     double dt;
     unsigned long long ready_prefix;    // slots below this index were written by the host side
+    uint32_t epoch;                     // value of a slot's ready word once it is fully written this cycle
+    int check_geometry;                 // 1: evaluate both geometry paths and count disagreements
 };
 
 // launchers implemented twice in track_kernels.cu (validation: --fmad=false + strict math; fast)

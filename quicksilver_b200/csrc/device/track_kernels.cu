@@ -2,15 +2,25 @@
 //
 // One persistent kernel follows particle histories to census / absorption / escape / rank exit
 // (reference: CycleTrackingGuts + CycleTrackingFunction, src/CycleTracking.cc:15-119).  Each lane owns one
-// in-flight particle held in registers; when a history ends the lane refills from the processing
-// vault (warp-aggregated claim), so warps stay full until the vault drains.  Fission secondaries are
-// appended to the same vault and picked up by whichever lane refills next; the fissioning parent is
-// "re-queued" in place (the reference sends it through the extra vault and MC_Load_Particle again,
-// src/CollisionEvent.cc:137-142 -- here the same reload transform is applied in registers).
+// in-flight particle held in registers.  Work distribution is a ticket queue over the processing vault:
+// an idle lane takes the next ticket (one warp-aggregated atomicAdd, never a CAS loop) and redeems it as
+// soon as that slot has been written -- by the host (initial vault, arrivals) or by a fission elsewhere on
+// the GPU (secondaries are appended to the same vault).  A single "inflight" counter (histories created
+// minus histories finished) tells idle warps when the cycle has drained.  The fissioning parent is
+// re-queued in place: the reference sends it through the extra vault and MC_Load_Particle again
+// (src/CollisionEvent.cc:137-142); here the same reload transform is applied in registers.
 //
-// This file is compiled twice (csrc/Makefile): QSB_VALIDATION=1 with --fmad=false and the portable
-// log/sin/cos of qs_strict_math.h (bit-comparable with the CPU oracle), QSB_VALIDATION=0 with FMA
-// contraction and the CUDA math library.
+// Geometry: the mesh is a uniform brick grid, so the nearest-facet search (24 ray/triangle tests in the
+// reference, src/MCT.cc:550-621) is done as a filtered exact predicate: the exit face and the triangle on
+// it are found with ordinary box arithmetic and a 1e-6 safety margin, and only the winning facet's
+// distance is evaluated with the reference's exact expression on the bit-exact plane rebuilt from the
+// 64-byte CellRec.  Anything within the margin of an edge, a diagonal or the exit face itself takes the
+// full 24-facet path, which restates the reference statement by statement.  Both paths give the same
+// bits; tracking_mode bit 1 makes the kernel run both and count disagreements (tests use it).
+//
+// Compiled twice (csrc/Makefile): QSB_VALIDATION=1 with --fmad=false and the portable log/sin/cos of
+// qs_strict_math.h (bit-comparable with the CPU oracle), QSB_VALIDATION=0 with FMA contraction and the
+// CUDA math library.
 //
 // Reference map: segment outcome  src/MC_Segment_Outcome.cc:31-226
 //                nearest facet    src/MCT.cc:87-137,280-395,436-621
@@ -37,26 +47,36 @@ constexpr double kTinyDouble = 1.0e-13;
 constexpr double kSmallDouble = 1.0e-10;
 constexpr double kHugeDouble = 1.0e+75;
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr unsigned long long kNoTicket = ~0ull;
 
 // facet -> 3 of the cell's 14 points, and facet -> matching facet of the face neighbour (src/MC_Domain.cc:41-50)
 __constant__ int8_t c_facet_points[24][4] = {
     {1, 3, 8, 0},  {3, 7, 8, 0},  {7, 5, 8, 0},  {5, 1, 8, 0},  {0, 4, 9, 0},  {4, 6, 9, 0},  {6, 2, 9, 0},  {2, 0, 9, 0},
     {3, 2, 10, 0}, {2, 6, 10, 0}, {6, 7, 10, 0}, {7, 3, 10, 0}, {0, 1, 11, 0}, {1, 5, 11, 0}, {5, 4, 11, 0}, {4, 0, 11, 0},
     {4, 5, 12, 0}, {5, 7, 12, 0}, {7, 6, 12, 0}, {6, 4, 12, 0}, {0, 2, 13, 0}, {2, 3, 13, 0}, {3, 1, 13, 0}, {1, 0, 13, 0} };
-__constant__ int8_t c_opposing_facet[24] = { 7, 6, 5, 4, 3, 2, 1, 0, 12, 15, 14, 13, 8, 11, 10, 9, 20, 23, 22, 21, 16, 19, 18, 17 };
+// the facet of face `f` whose base is the face-rectangle edge e: 0 = low u, 1 = high u, 2 = low v, 3 = high v, where
+// (u, v) are the two in-face axes in x<y<z order (derived from c_facet_points; checked by tests/test_host_model.py)
+__constant__ int8_t c_facet_of_edge[6][4] = { {3, 1, 0, 2}, {4, 6, 7, 5}, {9, 11, 8, 10}, {15, 13, 12, 14}, {19, 17, 16, 18}, {20, 22, 23, 21} };
 
 struct Particle
 {
     double x, y, z, vx, vy, vz, alpha, beta, gamma;
-    double energy, weight, ttc, age, nmfp, nseg, total_xs;
+    double energy, weight, ttc, age, nmfp, nseg, total_xs, speed;
     uint64_t seed, id;
+    uint4 head;                 // first 16 bytes of the current cell's CellRec
     int cell, facet, group;
     int last_event, num_collisions, breed, species;
 };
 
+__device__ __forceinline__ int cell_ix(const uint4& h) { return (int)(h.x & 0xffffu); }
+__device__ __forceinline__ int cell_iy(const uint4& h) { return (int)(h.x >> 16); }
+__device__ __forceinline__ int cell_iz(const uint4& h) { return (int)(h.y & 0xffffu); }
+__device__ __forceinline__ int cell_material(const uint4& h) { return (int)((h.y >> 16) & 0xffu); }
+__device__ __forceinline__ int face_event(const uint4& h, int face) { return (int)((h.z >> (4 * face)) & 0xfu); }
+
 struct Counters     // per-thread balance tallies, flushed once per kernel (src/Tallies.hh:36-100)
 {
-    unsigned int segments, collisions, scatters, absorbs, fissions, produced, escapes, census, lookups;
+    unsigned int segments, collisions, scatters, absorbs, fissions, produced, escapes, census, lookups, slow, mismatch;
 };
 
 // one facet plane {A,B,C,D}: two 16-byte read-only loads
@@ -65,6 +85,11 @@ __device__ __forceinline__ double4 load_plane(const double4* __restrict__ p)
     const double2 lo = __ldg(reinterpret_cast<const double2*>(p));
     const double2 hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
     return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__device__ __forceinline__ uint4 load_cell_head(const DevImage& im, int cell)
+{
+    return __ldg(reinterpret_cast<const uint4*>(im.cells + cell));
 }
 
 __device__ __forceinline__ double m_log(double x)
@@ -101,14 +126,16 @@ __device__ __forceinline__ int energy_group(const DevImage& im, double energy)
     return low;
 }
 
+__device__ __forceinline__ double speed_of(const Particle& p) { return sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz); }
+
 // MC_Load_Particle + MC_Particle(const MC_Base_Particle&): src/MC_Load_Particle.cc:11-29,
 // src/MC_Base_Particle.hh:287-331
 __device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p, double dt, bool derive_direction)
 {
+    p.speed = speed_of(p);
     if (derive_direction)
     {
-        const double speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
-        const double factor = 1.0 / speed;
+        const double factor = 1.0 / p.speed;
         p.alpha = factor * p.vx; p.beta = factor * p.vy; p.gamma = factor * p.vz;
     }
     if (p.ttc <= 0.0) p.ttc += dt;
@@ -129,6 +156,7 @@ __device__ __forceinline__ void load_particle(const TrackArgs& a, unsigned long 
     p.last_event = t.x; p.num_collisions = t.y; p.breed = t.z; p.species = t.w;
     p.alpha = __ldcg(v.dirx + i); p.beta = __ldcg(v.diry + i); p.gamma = __ldcg(v.dirz + i);
     p.facet = 0; p.total_xs = 0.0;
+    p.head = load_cell_head(a.im, p.cell);
     reload_transform(a.im, p, a.dt, p.alpha != p.alpha);
 }
 
@@ -141,30 +169,28 @@ __device__ __forceinline__ void store_particle(const VaultView& v, unsigned long
     __stcg(v.seed + i, (unsigned long long)p.seed); __stcg(v.id + i, (unsigned long long)p.id);
     __stcg(v.cell + i, p.cell);
     __stcg(v.tags + i, make_int4(p.last_event, p.num_collisions, p.breed, p.species));
-    if (v.dirx)
-    {
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        __stcg(v.dirx + i, with_direction ? p.alpha : nan);
-        __stcg(v.diry + i, with_direction ? p.beta : nan);
-        __stcg(v.dirz + i, with_direction ? p.gamma : nan);
-    }
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    __stcg(v.dirx + i, with_direction ? p.alpha : nan);
+    __stcg(v.diry + i, with_direction ? p.beta : nan);
+    __stcg(v.dirz + i, with_direction ? p.gamma : nan);
 }
 
-// ---- nearest facet ---------------------------------------------------------------------------------
+// ---- nearest facet, full path --------------------------------------------------------------------------
 
 // ray / triangle test of one facet: src/MCT.cc:280-395
 __device__ __forceinline__ double distance_to_segment(double plane_tolerance, double dot, const double4 pl,
                                                       const double* __restrict__ n0, const double* __restrict__ n1,
-                                                      const double* __restrict__ n2, const Particle& p)
+                                                      const double* __restrict__ n2, double px, double py, double pz,
+                                                      double alpha, double beta, double gamma)
 {
     const double bb_tol = 1e-9;
-    const double numerator = -1.0 * (pl.x * p.x + pl.y * p.y + pl.z * p.z + pl.w);
+    const double numerator = -1.0 * (pl.x * px + pl.y * py + pl.z * pz + pl.w);
     if (numerator < 0.0 && numerator * numerator > plane_tolerance) return kHugeDouble;
 
     const double distance = numerator / dot;
-    const double ix = p.x + distance * p.alpha;
-    const double iy = p.y + distance * p.beta;
-    const double iz = p.z + distance * p.gamma;
+    const double ix = px + distance * alpha;
+    const double iy = py + distance * beta;
+    const double iz = pz + distance * gamma;
 
     const double ax = __ldg(n0), ay = __ldg(n0 + 1), az = __ldg(n0 + 2);
     const double bx = __ldg(n1), by = __ldg(n1 + 1), bz = __ldg(n1 + 2);
@@ -210,17 +236,19 @@ __device__ __forceinline__ double distance_to_segment(double plane_tolerance, do
     return kHugeDouble;
 }
 
-// all 24 facets of the cell, nearest positive hit, fallback + retry nudge: src/MCT.cc:436-621, :87-137
-__device__ __noinline__ void nearest_facet(const DevImage& im, Particle& p, int& out_facet, double& out_distance)
+// all 24 facets of the cell, nearest positive hit, fallback + retry nudge: src/MCT.cc:436-621, :87-137.
+// Cold path (and the only path when the mesh is not compact-encodable); may move the coordinate.
+__device__ __noinline__ void nearest_facet_full(const double4* __restrict__ planes, const double* __restrict__ nodes,
+                                                double* px, double* py, double* pz, double alpha, double beta, double gamma,
+                                                double nseg, int* out_facet, double* out_distance)
 {
-    const double4* __restrict__ planes = im.planes + (size_t)p.cell * 24;
-    const double* __restrict__ nodes = im.nodes + (size_t)p.cell * 42;
     int iteration = 0;
     double move_factor = 0.5 * kSmallDouble;
     int nf_facet; double nf_distance;
+    double x = *px, y = *py, z = *pz;
     for (;;)
     {
-        const double plane_tolerance = 1e-16 * (p.x * p.x + p.y * p.y + p.z * p.z);
+        const double plane_tolerance = 1e-16 * (x * x + y * y + z * z);
         nf_facet = 0; nf_distance = 1e80;
         int neg_facet = 0; double neg_distance = -kHugeDouble;
 #pragma unroll 1
@@ -228,10 +256,10 @@ __device__ __noinline__ void nearest_facet(const DevImage& im, Particle& p, int&
         {
             double t = kHugeDouble;
             const double4 pl = load_plane(planes + f);
-            const double dot = (pl.x * p.alpha + pl.y * p.beta + pl.z * p.gamma);
+            const double dot = (pl.x * alpha + pl.y * beta + pl.z * gamma);
             if (dot > 0.0)
                 t = distance_to_segment(plane_tolerance, dot, pl, nodes + 3 * c_facet_points[f][0],
-                                        nodes + 3 * c_facet_points[f][1], nodes + 3 * c_facet_points[f][2], p);
+                                        nodes + 3 * c_facet_points[f][1], nodes + 3 * c_facet_points[f][2], x, y, z, alpha, beta, gamma);
             // MCT_Nearest_Facet_Find_Nearest folded into the loop: same order, same comparisons
             if (t > 0.0) { if (t <= nf_distance) { nf_distance = t; nf_facet = f; } }
             else if (t > neg_distance) { neg_distance = t; neg_facet = f; }
@@ -239,15 +267,15 @@ __device__ __noinline__ void nearest_facet(const DevImage& im, Particle& p, int&
         if (nf_distance == kHugeDouble && neg_distance != -kHugeDouble) { nf_distance = neg_distance; nf_facet = neg_facet; }
 
         bool retry = false;
-        if ((nf_distance == kHugeDouble && move_factor > 0) || (p.nseg > 10000000 && nf_distance <= 0.0))
+        if ((nf_distance == kHugeDouble && move_factor > 0) || (nseg > 10000000 && nf_distance <= 0.0))
         {
             double mx = 0, my = 0, mz = 0;
             for (int k = 0; k < 14; ++k) { mx += __ldg(nodes + 3 * k); my += __ldg(nodes + 3 * k + 1); mz += __ldg(nodes + 3 * k + 2); }
             const double inv = 1.0 / ((double)14);
             mx *= inv; my *= inv; mz *= inv;
-            p.x += move_factor * (mx - p.x);
-            p.y += move_factor * (my - p.y);
-            p.z += move_factor * (mz - p.z);
+            x += move_factor * (mx - x);
+            y += move_factor * (my - y);
+            z += move_factor * (mz - z);
             iteration++;
             move_factor *= 2.0;
             if (move_factor > 1.0e-2) move_factor = 1.0e-2;
@@ -256,22 +284,84 @@ __device__ __noinline__ void nearest_facet(const DevImage& im, Particle& p, int&
         if (!retry) break;
     }
     if (nf_distance < 0) nf_distance = 0;
-    out_facet = nf_facet; out_distance = nf_distance;
+    *px = x; *py = y; *pz = z;
+    *out_facet = nf_facet; *out_distance = nf_distance;
+}
+
+// ---- nearest facet, filtered fast path -----------------------------------------------------------------
+// Returns false when the configuration is within the safety margin of anything the reference treats with
+// tolerances (cell edges, face diagonals, the exit face itself, a particle outside its cell); the caller then
+// takes the full path.  When it returns true, (facet, distance) carry exactly the bits of the full path.
+__device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Particle& p, int& facet, double& distance)
+{
+    const int ix = cell_ix(p.head), iy = cell_iy(p.head), iz = cell_iz(p.head);
+    // exact node coordinates of the cell's corners: index * cell size (src/GlobalFccGrid.cc:112-131)
+    const double x0 = ix * im.dx, x1 = (ix + 1) * im.dx;
+    const double y0 = iy * im.dy, y1 = (iy + 1) * im.dy;
+    const double z0 = iz * im.dz, z1 = (iz + 1) * im.dz;
+    const double m = im.margin;
+    bool ok = p.x >= x0 - m && p.x <= x1 + m && p.y >= y0 - m && p.y <= y1 + m && p.z >= z0 - m && p.z <= z1 + m;
+
+    // gap to the candidate face of each axis (the face the direction points at) and |direction|
+    const double gx = p.alpha > 0 ? x1 - p.x : p.x - x0, ax = fabs(p.alpha);
+    const double gy = p.beta  > 0 ? y1 - p.y : p.y - y0, ay = fabs(p.beta);
+    const double gz = p.gamma > 0 ? z1 - p.z : p.z - z0, az = fabs(p.gamma);
+    // exit axis = argmin gap/|dir| over axes with dir != 0, by cross multiplication
+    int w = -1; double gw = 0, aw = 1;
+    if (ax > 0) { w = 0; gw = gx; aw = ax; }
+    if (ay > 0 && (w < 0 || gy * aw < gw * ay)) { w = 1; gw = gy; aw = ay; }
+    if (az > 0 && (w < 0 || gz * aw < gw * az)) { w = 2; gw = gz; aw = az; }
+    if (w < 0) return false;
+    ok = ok && gw > m;
+    const double t = gw / aw;                      // approximate distance: only used for the filter
+    const double ex = p.x + t * p.alpha, ey = p.y + t * p.beta, ez = p.z + t * p.gamma;
+
+    // normalised in-face coordinates of the exit point, (u, v) = the two other axes in x<y<z order
+    double su, sv, pw, dw, c_lo, c_hi;
+    if (w == 0)      { su = (ey - (y0 + 0.5 * im.dy)) * im.inv_hy; sv = (ez - (z0 + 0.5 * im.dz)) * im.inv_hz; pw = p.x; dw = p.alpha; c_lo = x0; c_hi = x1; }
+    else if (w == 1) { su = (ex - (x0 + 0.5 * im.dx)) * im.inv_hx; sv = (ez - (z0 + 0.5 * im.dz)) * im.inv_hz; pw = p.y; dw = p.beta;  c_lo = y0; c_hi = y1; }
+    else             { su = (ex - (x0 + 0.5 * im.dx)) * im.inv_hx; sv = (ey - (y0 + 0.5 * im.dy)) * im.inv_hy; pw = p.z; dw = p.gamma; c_lo = z0; c_hi = z1; }
+    const double au = fabs(su), av = fabs(sv);
+    const double mm = 1e-6;
+    ok = ok && fmax(au, av) < 1.0 - mm && fabs(au - av) > mm;
+    if (!ok) return false;
+
+    const int face = 2 * w + (dw > 0 ? 0 : 1);
+    const int edge = au > av ? (su > 0 ? 1 : 0) : (sv > 0 ? 3 : 2);
+    const int f = c_facet_of_edge[face][edge];
+
+    // rebuild the facet's exact plane from its code and evaluate the reference's expression for this facet only:
+    // numerator = -1.0 * (A*x + B*y + C*z + D) and dot = A*alpha + B*beta + C*gamma with B = C = (+-)0 reduce to
+    // the non-zero axis term (adding a signed zero to a non-zero double is exact)
+    const unsigned code = __ldg(im.cells[p.cell].code + f);
+    const double sign = (face & 1) ? -1.0 : 1.0;
+    const double normal = sign * ((code & 1u) ? __longlong_as_double(0x3FEFFFFFFFFFFFFFll) : 1.0);
+    const double coord = (face & 1) ? c_lo : c_hi;
+    const int k = (int)((code >> 1) & 3u);
+    const double d_abs = __longlong_as_double(__double_as_longlong(coord) + (k == 1 ? 1ll : (k == 2 ? -1ll : 0ll)));
+    const double D = (face & 1) ? d_abs : -d_abs;
+    const double numerator = -1.0 * (normal * pw + D);
+    const double dot = normal * dw;
+    const double dist = numerator / dot;
+    if (!(fabs(dist - t) <= 1e-9 * (t + m))) return false;   // also catches NaN
+    facet = f; distance = dist;
+    return true;
 }
 
 // ---- segment outcome: 0 collision, 1 facet crossing, 2 census -----------------------------------------
-__device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p)
+__device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, Counters& c)
 {
     const DevImage& im = a.im;
-    const double particle_speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+    const double particle_speed = p.speed;
 
     bool force_collision = false;
     if (p.nmfp < 0.0) { force_collision = true; p.nmfp = kSmallDouble; }
 
-    const int mat = __ldg(im.cell_material + p.cell);
-    const double xs = __ldg(im.xs_total + (size_t)mat * im.n_groups + p.group);
-    p.total_xs = xs;
-    const double mean_free_path = (xs == 0.0) ? kHugeDouble : 1.0 / xs;
+    // weightedMacroscopicCrossSection (src/MacroscopicCrossSection.cc:59-80): the reference's per-cell cache holds
+    // the same number for every cell of a material; {total, 1/total} are precomputed per (material, group)
+    const double2 xs = __ldg(im.xs_pair + (size_t)cell_material(p.head) * im.n_groups + p.group);
+    p.total_xs = xs.x;
+    const double mean_free_path = (xs.x == 0.0) ? kHugeDouble : xs.y;
 
     if (p.nmfp == 0.0)
     {
@@ -281,8 +371,20 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p)
 
     double d_collision = force_collision ? kSmallDouble : p.nmfp * mean_free_path;
     double d_census = particle_speed * p.ttc;
-    int nf_facet; double d_facet;
-    nearest_facet(im, p, nf_facet, d_facet);
+
+    int nf_facet = 0; double d_facet = 0.0;
+    const bool fast = im.compact && nearest_facet_fast(im, p, nf_facet, d_facet);
+    if (!fast || (a.check_geometry != 0))
+    {
+        int f2; double d2;
+        double qx = p.x, qy = p.y, qz = p.z;
+        nearest_facet_full(im.planes + (size_t)p.cell * 24, im.nodes + (size_t)p.cell * 42, &qx, &qy, &qz,
+                           p.alpha, p.beta, p.gamma, p.nseg, &f2, &d2);
+        if (fast) { if (f2 != nf_facet || d2 != d_facet || qx != p.x || qy != p.y || qz != p.z) c.mismatch++; }
+        else { c.slow++; }
+        p.x = qx; p.y = qy; p.z = qz;
+        nf_facet = f2; d_facet = d2;
+    }
     if (force_collision) { d_facet = kHugeDouble; d_census = kHugeDouble; d_collision = kTinyDouble; }
 
     // MC_Find_Min: strict <, ties to the lower index
@@ -342,35 +444,72 @@ __device__ __forceinline__ void update_trajectory(double energy, double angle, P
     p.nmfp = -1.0 * m_log(r);
 }
 
-// append a secondary to the processing vault; it becomes claimable once its ready word carries the epoch
-__device__ __forceinline__ void push_secondary(const TrackArgs& a, const Particle& child)
+// append a secondary to the processing vault: count it in flight, write it, then publish the slot
+__device__ __forceinline__ void push_secondary(const TrackArgs& a, const Particle& child, uint32_t epoch)
 {
     const unsigned long long slot = atomicAdd(&a.ctl->tail, 1ull);
     if (slot >= a.proc.capacity) { atomicOr(&a.ctl->overflow, 1u); return; }
+    atomicAdd(&a.ctl->inflight, 1ull);
     store_particle(a.proc, slot, child, false);
     __threadfence();
-    *((volatile uint32_t*)(a.proc.ready + slot)) = a.ctl->epoch;
+    *((volatile uint32_t*)(a.proc.ready + slot)) = epoch;
+}
+
+// The reference walks the material's (isotope, reaction) table subtracting each macroscopic cross section until
+// the running value goes negative (src/CollisionEvent.cc:59-83).  Every isotope of a material carries the same
+// reaction table (src/initMC.cc:160-196; checked per material on the host), so the NR per-reaction values are
+// held in registers and the same subtraction chain runs without further loads.  Returns the flat index
+// iso * n_react + react, or -1.
+template <int NR>
+__device__ __forceinline__ int select_reaction_periodic(const double* __restrict__ table, int n_iso, int n_react, double current)
+{
+    double v[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) v[k] = (k < n_react) ? __ldg(table + k) : 0.0;
+    for (int iso = 0; iso < n_iso; ++iso)
+    {
+        double run[NR];
+        double cur = current;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) { cur = cur - v[k]; run[k] = cur; }
+        if (cur < 0)
+        {
+            // values are non-negative, so the chain is non-increasing: the first negative entry is the selection
+            int first = NR - 1;
+#pragma unroll
+            for (int k = NR - 2; k >= 0; --k) if (run[k] < 0) first = k;
+            return iso * n_react + first;
+        }
+        current = cur;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int select_reaction_generic(const double* __restrict__ table, int n_total, double current)
+{
+    for (int k = 0; k < n_total; ++k)
+    {
+        current -= __ldg(table + k);
+        if (current < 0) return k;
+    }
+    return -1;
 }
 
 // returns true when the particle keeps tracking
-__device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p, Counters& c)
+__device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p, Counters& c, uint32_t epoch)
 {
     const DevImage& im = a.im;
-    const int mat = __ldg(im.cell_material + p.cell);
+    const int mat = cell_material(p.head);
     const double* __restrict__ table = im.xs_react + ((size_t)mat * im.n_groups + p.group) * im.max_react;
-    const int n_react_total = __ldg(im.mat_n_iso + mat) * __ldg(im.mat_n_react + mat);
+    const int n_iso = __ldg(im.mat_n_iso + mat), n_react = __ldg(im.mat_n_react + mat);
 
     double r = qs_rng_sample(&p.seed);
-    double current = p.total_xs * r;
-    // the reference's nested isotope/reaction loop visits the table in storage order and leaves both
-    // loops at the first negative running value (src/CollisionEvent.cc:67-83)
-    int selected = -1;
-    for (int k = 0; k < n_react_total; ++k)
-    {
-        current -= __ldg(table + k);
-        if (current < 0) { selected = k; break; }
-    }
-    c.lookups += (selected < 0 ? n_react_total : selected + 1);
+    const double current = p.total_xs * r;
+    int selected;
+    if (__ldg(im.mat_periodic + mat) && n_react <= 3)      selected = select_reaction_periodic<3>(table, n_iso, n_react, current);
+    else if (__ldg(im.mat_periodic + mat) && n_react <= 9) selected = select_reaction_periodic<9>(table, n_iso, n_react, current);
+    else                                                   selected = select_reaction_generic(table, n_iso * n_react, current);
+    c.lookups += (selected < 0 ? n_iso * n_react : selected + 1);
     if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return false; }
 
     double energyOut[4], angleOut[4];
@@ -409,17 +548,15 @@ __device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p,
 
     if (nOut == 0) return false;
 
-#pragma unroll
-    for (int s = 1; s < 4; ++s)
+#pragma unroll 1
+    for (int s = 1; s < nOut; ++s)
     {
-        if (s < nOut)
-        {
-            Particle child = p;
-            child.seed = qs_rng_spawn(&p.seed);
-            child.id = child.seed;
-            update_trajectory(energyOut[s], angleOut[s], child);
-            push_secondary(a, child);
-        }
+        Particle child = p;
+        child.seed = qs_rng_spawn(&p.seed);
+        child.id = child.seed;
+        update_trajectory(s == 1 ? energyOut[1] : (s == 2 ? energyOut[2] : energyOut[3]),
+                          s == 1 ? angleOut[1] : (s == 2 ? angleOut[2] : angleOut[3]), child);
+        push_secondary(a, child, epoch);
     }
     update_trajectory(energyOut[0], angleOut[0], p);
     if (nOut > 1)
@@ -429,6 +566,7 @@ __device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p,
         reload_transform(im, p, a.dt, true);
         return true;
     }
+    p.speed = speed_of(p);
     p.group = energy_group(im, p.energy);
     return true;
 }
@@ -444,8 +582,9 @@ __device__ __forceinline__ void reflect_particle(const DevImage& im, Particle& p
         p.beta  -= dot * pl.y;
         p.gamma -= dot * pl.z;
     }
-    const double speed = sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz);
+    const double speed = p.speed;
     p.vx = speed * p.alpha; p.vy = speed * p.beta; p.vz = speed * p.gamma;
+    p.speed = speed_of(p);
 }
 
 __device__ __forceinline__ int flat_to_domain(const DevImage& im, int flat)
@@ -471,13 +610,19 @@ __device__ __forceinline__ void fill_base(const DevImage& im, const Particle& p,
 __device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particle& p, Counters& c)
 {
     const DevImage& im = a.im;
-    const size_t k = (size_t)p.cell * 6 + (p.facet >> 2);
-    const int event = __ldg(im.face_event + k);
+    const int face = p.facet >> 2;
+    const int event = face_event(p.head, face);
     if (event == QSB_ADJ_TRANSIT_ON)
     {
-        p.cell = __ldg(im.face_adj_cell + k);
-        p.facet = c_opposing_facet[p.facet];
+        p.cell = __ldg(im.cells[p.cell].adj + face);
+        p.head = load_cell_head(im, p.cell);
         p.last_event = QSB_EV_FACET_TRANSIT;
+        return true;
+    }
+    if (event == QSB_ADJ_REFLECT)
+    {
+        p.last_event = QSB_EV_REFLECTION;
+        reflect_particle(im, p);
         return true;
     }
     if (event == QSB_ADJ_ESCAPE)
@@ -487,15 +632,10 @@ __device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particl
         c.escapes++;
         return false;
     }
-    if (event == QSB_ADJ_REFLECT)
-    {
-        p.last_event = QSB_EV_REFLECTION;
-        reflect_particle(im, p);
-        return true;
-    }
     if (event == QSB_ADJ_TRANSIT_OFF)
     {
         p.last_event = QSB_EV_COMMUNICATION;
+        const size_t k = (size_t)p.cell * 6 + face;
         const int rank = __ldg(im.face_nbr_rank + k);
         const unsigned long long slot = atomicAdd(&a.ctl->send_count[rank], 1ull);
         if (slot >= a.send_capacity) { atomicOr(&a.ctl->overflow, 4u); return false; }
@@ -525,63 +665,70 @@ template <int kDummy>
 __global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ TrackArgs a)
 {
     const unsigned lane = threadIdx.x & 31u;
-    Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     Particle p;
     bool have = false;
-    const uint32_t epoch = a.ctl->epoch;
+    unsigned long long ticket = kNoTicket;
+    const uint32_t epoch = a.epoch;
+    unsigned backoff = 64;
 
     for (;;)
     {
         __syncwarp();
-        const unsigned need = __ballot_sync(kFullMask, !have);
-        if (need)
+        // 1. every idle lane without a ticket takes the next one: one atomicAdd per warp
+        const bool want = !have && ticket == kNoTicket;
+        const unsigned want_mask = __ballot_sync(kFullMask, want);
+        if (want_mask)
         {
-            // warp-aggregated claim of up to popc(need) consecutive slots; never past the allocated tail
-            unsigned long long base = 0; int got = 0;
-            if (lane == 0)
-            {
-                const int want = __popc(need);
-                unsigned long long h = *((volatile unsigned long long*)&a.ctl->head);
-                for (;;)
-                {
-                    unsigned long long t = *((volatile unsigned long long*)&a.ctl->tail);
-                    if (t > a.proc.capacity) t = a.proc.capacity;
-                    if (h >= t) { got = 0; break; }
-                    const unsigned long long n = (t - h < (unsigned long long)want) ? (t - h) : (unsigned long long)want;
-                    const unsigned long long old = atomicCAS(&a.ctl->head, h, h + n);
-                    if (old == h) { base = h; got = (int)n; break; }
-                    h = old;
-                }
-            }
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&a.ctl->head, (unsigned long long)__popc(want_mask));
             base = __shfl_sync(kFullMask, base, 0);
-            got = __shfl_sync(kFullMask, got, 0);
-            if (!have)
-            {
-                const int rank = __popc(need & ((1u << lane) - 1u));
-                if (rank < got)
-                {
-                    const unsigned long long idx = base + rank;
-                    if (idx >= a.ready_prefix)
-                        while (*((volatile uint32_t*)(a.proc.ready + idx)) != epoch) { __nanosleep(64); }
-                    __threadfence();
-                    load_particle(a, idx, p);
-                    have = true;
-                }
-            }
-            if (__ballot_sync(kFullMask, have) == 0u) break;     // vault drained (for now): the host re-launches if secondaries remain
+            if (want) ticket = base + __popc(want_mask & ((1u << lane) - 1u));
         }
+        // 2. redeem: the slot is ready if the host wrote it (below ready_prefix) or its ready word carries this epoch
+        if (!have && ticket != kNoTicket && ticket < a.proc.capacity)
+        {
+            bool ready = ticket < a.ready_prefix;
+            if (!ready) ready = *((volatile uint32_t*)(a.proc.ready + ticket)) == epoch;
+            if (ready)
+            {
+                __threadfence();
+                load_particle(a, ticket, p);
+                have = true;
+                ticket = kNoTicket;
+            }
+        }
+        const unsigned have_mask = __ballot_sync(kFullMask, have);
+        if (have_mask == 0u)
+        {
+            // idle warp: the cycle is over when no history is queued or running anywhere on this GPU
+            unsigned long long inflight = 1;
+            if (lane == 0) inflight = *((volatile unsigned long long*)&a.ctl->inflight);
+            inflight = __shfl_sync(kFullMask, inflight, 0);
+            if (inflight == 0ull) break;
+            __nanosleep(backoff);
+            if (backoff < 2048) backoff *= 2;
+            continue;
+        }
+        backoff = 64;
 
+        bool finished = false;
         if (have)
         {
-            const int outcome = segment_outcome(a, p);
+            const int outcome = segment_outcome(a, p, c);
             c.segments++;
             p.nseg += 1.;
             bool keep;
-            if (outcome == 0) keep = collision_event(a, p, c);
+            if (outcome == 0) keep = collision_event(a, p, c, epoch);
             else if (outcome == 1) keep = facet_crossing_event(a, p, c);
             else { census_event(a, p, c); keep = false; }
             have = keep;
+            finished = !keep;
         }
+        // 3. retire finished histories: one reduction per warp.  Secondaries were counted before they became
+        //    visible (push_secondary), so inflight reaches 0 only when nothing is queued or running.
+        const unsigned fin_mask = __ballot_sync(kFullMask, finished);
+        if (fin_mask && lane == 0) atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)__popc(fin_mask));
     }
 
     // flush the per-thread balance counters: warp sum, one atomic per counter per warp
@@ -589,6 +736,7 @@ __global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ T
     const unsigned int s_seg = warp_sum(c.segments), s_col = warp_sum(c.collisions), s_sca = warp_sum(c.scatters);
     const unsigned int s_abs = warp_sum(c.absorbs), s_fis = warp_sum(c.fissions), s_pro = warp_sum(c.produced);
     const unsigned int s_esc = warp_sum(c.escapes), s_cen = warp_sum(c.census), s_look = warp_sum(c.lookups);
+    const unsigned int s_slow = warp_sum(c.slow), s_mis = warp_sum(c.mismatch);
     if (lane == 0)
     {
         unsigned long long* b = a.ctl->balance;
@@ -601,6 +749,8 @@ __global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ T
         if (s_esc) atomicAdd(b + QSB_BAL_ESCAPE, (unsigned long long)s_esc);
         if (s_cen) atomicAdd(b + QSB_BAL_CENSUS, (unsigned long long)s_cen);
         if (s_look) atomicAdd(&a.ctl->n_lookups, (unsigned long long)s_look);
+        if (s_slow) atomicAdd(&a.ctl->slow_geometry, (unsigned long long)s_slow);
+        if (s_mis) atomicAdd(&a.ctl->geometry_mismatch, (unsigned long long)s_mis);
     }
 }
 

@@ -11,10 +11,10 @@ from ._capi import BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE, QsbError
 
 class DeviceContext:
     def __init__(self, image, dt, device=0, validation=True, particle_capacity=0, send_capacity=0,
-                 threads_per_block=0, blocks_per_sm=0):
+                 threads_per_block=0, blocks_per_sm=0, check_geometry=False):
         self._lib = _capi.lib()
         self.image = image
-        self.opt = _capi.Options(int(bool(validation)), 0, int(particle_capacity), int(send_capacity),
+        self.opt = _capi.Options(int(bool(validation)), 2 if check_geometry else 0, int(particle_capacity), int(send_capacity),
                                  int(threads_per_block), int(blocks_per_sm))
         self._h = C.c_void_p()
         rc = self._lib.qsb_create(int(device), C.byref(image), float(dt), C.byref(self.opt), C.byref(self._h))
@@ -91,6 +91,13 @@ class DeviceContext:
 
     def put_arrivals(self, device_ptr, n):
         self._check(self._lib.qsb_put_arrivals(self._h, C.c_void_p(device_ptr), int(n)))
+
+    def diagnostics(self):
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.qsb_get_diagnostics(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        keys = ("slow_geometry", "geometry_mismatch", "reaction_lookups", "compact_geometry", "registers",
+                "blocks_per_sm", "grid", "vault_slots_used")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def launch_count(self):
         return int(self._lib.qsb_launch_count(self._h))

@@ -25,12 +25,12 @@ CASES = {
 }
 
 
-def _run_case(tmp_path, name, validation=True):
+def _run_case(tmp_path, name, validation=True, check_geometry=False):
     deck_name, over, cycles = CASES[name]
     deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
     mc = host.MonteCarlo(["-i", deck])
     dt = mc.get_double("dt")
-    ctx = device.DeviceContext(mc.image, dt, validation=validation, particle_capacity=1 << 20)
+    ctx = device.DeviceContext(mc.image, dt, validation=validation, particle_capacity=1 << 20, check_geometry=check_geometry)
     out = []
     for _ in range(cycles):
         mc.cycle_init()
@@ -41,6 +41,7 @@ def _run_case(tmp_path, name, validation=True):
         census, balance, flux = ctx.get_census(), ctx.get_balance(), ctx.get_scalar_flux()
         flux_sum = ctx.scalar_flux_sum()
         want = H.oracle_track(mc.image, dt, vault, strict=True, threads=1)
+        stats.diag = ctx.diagnostics()
         out.append((census, balance, flux, flux_sum, want, stats))
         # carry the ORACLE's census forward so every cycle starts from identical inputs
         mc.set_tracking_result(want.census, want.balance, want.flux.sum())
@@ -61,6 +62,18 @@ def test_validation_build_matches_oracle_bit_for_bit(tmp_path, name):
         assert np.allclose(flux, want.flux, rtol=FLUX_RTOL, atol=0.0)
         assert abs(flux_sum - want.flux.sum()) <= 1e-11 * abs(want.flux.sum())
         assert stats.n_processed >= len(census)
+
+
+@pytest.mark.parametrize("name", ["cts2_small", "p2_small", "allescape_4dom", "nofission_octant"])
+def test_filtered_geometry_agrees_with_full_search(tmp_path, name):
+    """check mode: every segment evaluates both the filtered single-facet path and the reference's full
+    24-facet search; they must agree on facet, distance and coordinate bit for bit, and the filtered path
+    must carry nearly all segments."""
+    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_geometry=True):
+        assert stats.diag["compact_geometry"] == 1
+        assert stats.diag["geometry_mismatch"] == 0
+        assert stats.diag["slow_geometry"] <= 0.01 * float(balance[BAL["num_segments"]]) + 10
+        assert np.array_equal(balance, want.balance)
 
 
 @pytest.mark.parametrize("name", ["cts2_small", "p1_small"])
