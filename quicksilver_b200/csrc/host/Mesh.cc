@@ -235,6 +235,33 @@ void initMesh(const Parameters& params, const MaterialDatabase& db, int myRank, 
         d.material.resize(n); d.volume.resize(n); d.cellId.resize(n); d.sourceTally.assign(n, 0);
     }
 
+    auto materialAt = [&](const double* nodes) {
+        const Vec3 where = cellPosition(nodes);
+        std::string matName;                                   // last geometry containing the point wins
+        for (const GeometryParameters& geom : params.geometryParams)
+            if (inside(geom, where)) matName = geom.materialName;
+        const int mat = db.findMaterial(matName);
+        if (mat < 0) throw std::runtime_error("a mesh cell lies in no geometry / unknown material '" + matName + "'");
+        return mat;
+    };
+
+    // Several ranks: every rank also evaluates volume * sourceRate of EVERY global cell, in global-id order, so that
+    // the total source weight (src/MC_SourceNow.cc:41-57) can be summed in one canonical order on all ranks and an
+    // N-rank run reproduces the single-rank run bit for bit instead of depending on an allreduce's rounding.
+    ddc.globalVolumeRate.clear();
+    if (nRanks > 1)
+    {
+        ddc.globalVolumeRate.resize(nGlobal);
+        for (int64_t g = 0; g < nGlobal; ++g)
+        {
+            Vec3 pts[14];
+            double nodes[42];
+            grid.cellNodes(g, pts);
+            for (int p = 0; p < 14; ++p) { nodes[3 * p] = pts[p].x; nodes[3 * p + 1] = pts[p].y; nodes[3 * p + 2] = pts[p].z; }
+            ddc.globalVolumeRate[g] = cellVolume(nodes) * db.mat[materialAt(nodes)].sourceRate;
+        }
+    }
+
     for (int64_t g = 0; g < nGlobal; ++g)
     {
         if (ddc.rankOf(owner[g]) != myRank) continue;
@@ -266,13 +293,7 @@ void initMesh(const Parameters& params, const MaterialDatabase& db, int myRank, 
         }
 
         d.volume[c] = cellVolume(nodes);
-        const Vec3 where = cellPosition(nodes);
-        std::string matName;                                   // last geometry containing the point wins
-        for (const GeometryParameters& geom : params.geometryParams)
-            if (inside(geom, where)) matName = geom.materialName;
-        const int mat = db.findMaterial(matName);
-        if (mat < 0) throw std::runtime_error("a mesh cell lies in no geometry / unknown material '" + matName + "'");
-        d.material[c] = mat;
+        d.material[c] = materialAt(nodes);
 
         Vec3 centre = { 0., 0., 0. };                          // src/MC_Domain.cc:321-330 (divide, not multiply)
         for (int p = 0; p < 14; ++p) { centre.x += pts[p].x; centre.y += pts[p].y; centre.z += pts[p].z; }

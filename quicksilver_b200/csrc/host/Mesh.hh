@@ -68,6 +68,7 @@ struct DecompositionInfo
     int nRanks = 1, myRank = 0, nDomainsPerRank = 1;
     std::vector<Vec3> centers;           // one per global domain
     std::vector<int> myDomainGids;
+    std::vector<double> globalVolumeRate; // nRanks > 1 only: volume * sourceRate of every global cell, by global id
     int rankOf(int domainGid) const { return domainGid / nDomainsPerRank; }      // src/DecompositionObject.cc:41-45
     int indexOf(int domainGid) const { return domainGid % nDomainsPerRank; }
 };

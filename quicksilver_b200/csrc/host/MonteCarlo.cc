@@ -208,7 +208,13 @@ void sourceNow(MonteCarlo& mc)
         for (int c = 0; c < d.nCells; ++c)
             localWeight += d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
     double totalWeight = localWeight;
-    mc.reduceSum(&totalWeight, 1);
+    if (!mc.ddc.globalVolumeRate.empty())
+    {
+        // several ranks: the same sum over ALL cells in global-id order on every rank (no allreduce rounding)
+        totalWeight = 0;
+        for (double vr : mc.ddc.globalVolumeRate) totalWeight += vr * dt;
+    }
+    else mc.reduceSum(&totalWeight, 1);
 
     const double sourceFraction = 0.1;
     const double weight = totalWeight / (sourceFraction * sp.nParticles);

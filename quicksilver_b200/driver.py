@@ -112,10 +112,17 @@ def exchange_rounds(backend, dist, rank, world, max_rounds=100000):
 class Simulation:
     """One rank of a run: host model + device context + the cycle loop."""
 
-    def __init__(self, argv, rank=0, world=1, device=0, validation=True, dist=None, particle_capacity=0, send_capacity=0):
+    def __init__(self, argv, rank=0, world=1, device=0, validation=True, dist=None, particle_capacity=0, send_capacity=0,
+                 make_backend=None):
+        """make_backend(mc) -> tracking backend; None = the device (the product path).  Tests of the exchange
+        protocol pass a CPU stand-in so that the N-rank logic runs under gloo on a machine without GPUs."""
         self.rank, self.world, self.dist = rank, world, dist
         self.torch_device = "cuda:%d" % device
         self.mc = host_mod.MonteCarlo(argv, rank, world, allreduce=self._allreduce if world > 1 else None)
+        self.ctx = None
+        if make_backend is not None:
+            self.backend = make_backend(self.mc)
+            return
         n_particles = self.mc.get_int("nParticles")
         if particle_capacity == 0:
             per_rank = (n_particles + world - 1) // world
@@ -140,7 +147,7 @@ class Simulation:
         self.mc.cycle_init()
         t1 = time.perf_counter()
         info = {}
-        if self.world == 1:
+        if self.world == 1 and self.ctx is not None:
             stats = self.mc.cycle_tracking(self.ctx)
             info.update(device_ms=stats.device_ms, launches=stats.n_launches, rounds=1)
         else:
@@ -157,7 +164,8 @@ class Simulation:
         return row, flux, info
 
     def close(self):
-        self.ctx.close()
+        if self.ctx is not None:
+            self.ctx.close()
         self.mc.close()
 
 

@@ -1,0 +1,45 @@
+"""Worker of tests/test_exchange_gloo.py: one rank of a domain-decomposed run under torch.distributed (gloo),
+tracking done by the CPU oracle through the same driver code (quicksilver_b200.driver.exchange_rounds /
+Simulation) that drives the GPUs under NCCL.  Rank 0 writes the global cycle rows and every rank writes its census
+(cells as global ids) to the output directory."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch.distributed as dist
+    import helpers as H
+    from quicksilver_b200 import driver
+
+    out_dir, cycles = sys.argv[1], int(sys.argv[2])
+    argv = sys.argv[3:]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo")
+    sim = driver.Simulation(argv, rank, world, dist=dist,
+                            make_backend=lambda mc: H.OracleBackend(mc.image, mc.get_double("dt"), rank, world, strict=False))
+    rows, info = [], []
+    gid = sim.mc.image.array("cell_gid")
+    for c in range(cycles):
+        row, flux, meta = sim.cycle()
+        rows.append([int(v) for v in row] + [flux])
+        info.append({"rounds": meta["rounds"], "sent": meta["sent"]})
+        census, _, _ = sim.backend.results()
+        census = census.copy()
+        census["cell"] = gid[census["cell"]]
+        census["domain"] = 0
+        np.save(os.path.join(out_dir, "census_c%d_r%d.npy" % (c, rank)), census)
+    with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
+        json.dump({"rows": rows, "info": info}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -118,3 +118,69 @@ def golden_table(name):
     import json
     with open(os.path.join(GOLDEN, "balance_tables.json")) as f:
         return [(r[0], r[1]) for r in json.load(f)[name]["rows"]]
+
+
+# ---- golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from the reference) ------
+
+def golden_case(case):
+    return np.load(os.path.join(GOLDEN, case + ".npz"))
+
+
+def golden_deck(case, tmp_path):
+    """the deck a fixture was generated from (tests/golden/make_golden.py: CASES)."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden
+    from quicksilver_b200 import decks
+    return decks.write_deck(make_golden.deck_of(case), os.path.join(str(tmp_path), case + ".inp"))
+
+
+# ---- CPU stand-in for the device backend of quicksilver_b200.driver (tests of the exchange protocol) ------
+
+class OracleBackend:
+    """Same interface as driver.DeviceBackend, tracking done by the CPU oracle.  Lets the N-rank exchange /
+    termination protocol of driver.exchange_rounds run under gloo on a machine without GPUs."""
+
+    def __init__(self, image, dt, rank, world, strict=False):
+        self.image, self.dt, self.rank, self.world, self.strict = image, dt, rank, world, strict
+        self.torch_device = "cpu"
+
+    def begin(self, vault):
+        self.pending = np.ascontiguousarray(vault, dtype=PARTICLE_DTYPE)
+        self.arrivals = np.zeros(0, EXCHANGE_DTYPE)
+        self.census = []
+        self.balance = np.zeros(BAL_COUNT, np.uint64)
+        self.flux = np.zeros((self.image.n_cells, self.image.n_groups))
+        self.sends = [np.zeros(0, EXCHANGE_DTYPE) for _ in range(self.world)]
+
+    def track(self):
+        r = oracle_track(self.image, self.dt, self.pending, arrivals=self.arrivals, strict=self.strict, threads=1)
+        self.pending = np.zeros(0, PARTICLE_DTYPE)
+        self.arrivals = np.zeros(0, EXCHANGE_DTYPE)
+        self.census.append(r.census)
+        self.balance += r.balance
+        self.flux += r.flux
+        for peer in range(self.world):
+            self.sends[peer] = np.concatenate([self.sends[peer], r.sends[r.send_rank == peer]])
+        return r
+
+    def send_counts(self):
+        return np.array([len(s) for s in self.sends], dtype=np.int64)
+
+    def send_tensor(self, peer, n):
+        import torch
+        assert len(self.sends[peer]) == n
+        return torch.from_numpy(np.ascontiguousarray(self.sends[peer]).view(np.uint8).reshape(-1).copy())
+
+    def recv_tensor(self, n):
+        import torch
+        return torch.empty(n * EXCHANGE_DTYPE.itemsize, dtype=torch.uint8)
+
+    def put_arrivals(self, tensor, n):
+        self.arrivals = np.concatenate([self.arrivals, tensor.numpy().view(EXCHANGE_DTYPE).reshape(-1)[:n].copy()])
+
+    def clear_sends(self):
+        self.sends = [np.zeros(0, EXCHANGE_DTYPE) for _ in range(self.world)]
+
+    def results(self):
+        census = np.concatenate(self.census) if self.census else np.zeros(0, PARTICLE_DTYPE)
+        return census, self.balance, float(self.flux.sum())
