@@ -21,9 +21,17 @@ def main():
     out_dir, cycles = sys.argv[1], int(sys.argv[2])
     argv = sys.argv[3:]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    dist.init_process_group("gloo")
-    sim = driver.Simulation(argv, rank, world, dist=dist,
-                            make_backend=lambda mc: H.OracleBackend(mc.image, mc.get_double("dt"), rank, world, strict=False))
+    if os.environ.get("QSB_TEST_BACKEND") == "device":
+        # the product path: validation kernels on one GPU per rank, NCCL for the exchange
+        import torch
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
+        sim = driver.Simulation(argv, rank, world, device=local, validation=True, dist=dist, particle_capacity=1 << 20)
+    else:
+        dist.init_process_group("gloo")
+        sim = driver.Simulation(argv, rank, world, dist=dist,
+                                make_backend=lambda mc: H.OracleBackend(mc.image, mc.get_double("dt"), rank, world, strict=False))
     rows, info = [], []
     gid = sim.mc.image.array("cell_gid")
     for c in range(cycles):
