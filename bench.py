@@ -142,6 +142,9 @@ def main():
     ap.add_argument("--fast", type=int, default=1, help="1: fast build kernels (default), 0: validation build")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU problem (testing only; reported in config)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--resident-only", type=int, default=0,
+                    help="1: skip the host-buffer (e2e) pass -- for ncu runs only: under the profiler a kernel launch does not return "
+                         "until the kernel has ended, so the streamed pass (kernel launched first, then fed by DMA) cannot make progress")
     args = ap.parse_args()
     warmup = max(args.warmup, 3)
 

@@ -148,6 +148,8 @@ int  qsb_mc_get_double(qsb_mc* mc, const char* key, double* out);     /* dt, lx,
 int  qsb_mc_cycle_init(qsb_mc* mc);
 /* processing vault (tracking input) as one contiguous AoS; valid until the next qsb_mc_* call. */
 int  qsb_mc_processing(qsb_mc* mc, const qsb_base_particle** aos, uint64_t* n);
+/* processed vault (this cycle's census, the next cycle's carried-over particles); n may be NULL. */
+int  qsb_mc_processed(qsb_mc* mc, const qsb_base_particle** aos, uint64_t* n);
 /* hand the tracker's result back: census particles become the processed vault, counters are added to
  * this cycle's balance task (only the tracking counters are read: absorb, census, escape, collision,
  * fission, produce, scatter, num_segments). */
@@ -169,9 +171,10 @@ typedef struct qsb_ctx qsb_ctx;
 
 typedef struct qsb_options {
     int32_t  validation;        /* 1: --fmad=false kernels + strict log/sin/cos (bit-exact vs oracle);
-                                   0: fast build (FMA contraction, CUDA libm)                          */
+                                   0: fast build (FMA contraction of the same source)                  */
     int32_t  tracking_mode;     /* bit 0 reserved (0: history-based persistent kernel); bit 1 (value 2): run the
-                                   filtered and the full nearest-facet search side by side and count mismatches  */
+                                   filtered and the full nearest-facet search side by side and count mismatches;
+                                   bit 2 (value 4): likewise for the direct reaction selection vs the subtraction chain */
     uint64_t particle_capacity; /* SoA slots per vault; 0 = derive from nParticles and nuBar            */
     uint64_t send_capacity;     /* slots per peer send/recv slab; 0 = derive                             */
     int32_t  threads_per_block; /* 0 = default                                                           */
@@ -195,6 +198,19 @@ int  qsb_cycle_begin(qsb_ctx* ctx, int keep_census);
 int  qsb_put_particles(qsb_ctx* ctx, const qsb_base_particle* aos, uint64_t n);
 /* run all local histories to exhaustion, secondaries included (src/main.cc:163-283 for one rank). */
 int  qsb_track(qsb_ctx* ctx, qsb_track_stats* stats);
+/* Host-buffer streaming: the same cycle with the copies overlapped with tracking.  qsb_stream_begin (directly after
+ * qsb_cycle_begin) names the cycle's input vault `in` and the buffer the census is to be delivered to; the next qsb_track
+ * launches the tracking kernel first and then feeds it: the host vault is DMA-copied in 8.9 MB chunks as it is (136-byte
+ * records, read directly by the kernel) while finished census chunks travel back the same way.  Buffers should be
+ * page-locked (the host model's vaults are); pageable ones are staged through an internal bounce buffer.  Further
+ * qsb_track calls of the same cycle (arrivals from other ranks) keep appending to the census; qsb_stream_end copies what is
+ * left and returns the census count.  If it exceeds census_cap the first census_cap records were delivered and the rest
+ * can be fetched with qsb_get_census_range.  qsb_track_host = begin + track + end (one rank). */
+int  qsb_stream_begin(qsb_ctx* ctx, const qsb_base_particle* in, uint64_t n_in, qsb_base_particle* census_out, uint64_t census_cap);
+int  qsb_stream_end(qsb_ctx* ctx, uint64_t* n_census);
+int  qsb_get_census_range(qsb_ctx* ctx, uint64_t first, qsb_base_particle* out, uint64_t count);
+int  qsb_track_host(qsb_ctx* ctx, const qsb_base_particle* in, uint64_t n_in, qsb_base_particle* census_out, uint64_t census_cap,
+                    uint64_t* n_census, qsb_track_stats* stats);
 int  qsb_census_count(qsb_ctx* ctx, uint64_t* n);
 int  qsb_get_census(qsb_ctx* ctx, qsb_base_particle* aos, uint64_t cap, uint64_t* n);
 int  qsb_get_balance(qsb_ctx* ctx, uint64_t out[QSB_BAL_COUNT]);
@@ -209,7 +225,7 @@ int  qsb_clear_sends(qsb_ctx* ctx);
 int  qsb_put_arrivals(qsb_ctx* ctx, const void* device_records, uint64_t n_records);
 uint64_t qsb_exchange_record_bytes(void);
 const char* qsb_last_error(qsb_ctx* ctx);
-/* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] fast/full geometry
+/* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] check-mode (geometry or reaction)
  * disagreements (check mode; must be 0), [2] reaction-table entries scanned, [3] compact geometry enabled,
  * [4] registers per thread, [5] resident blocks per SM, [6] grid size, [7] vault slots used. */
 int  qsb_get_diagnostics(qsb_ctx* ctx, uint64_t out[8]);
@@ -221,6 +237,11 @@ uint64_t qsb_launch_count(qsb_ctx* ctx);
  * track, census + balance + flux sum -> host model.  Host buffers in, host buffers out.
  * ==================================================================================================== */
 int  qsb_mc_cycle_tracking(qsb_mc* mc, qsb_ctx* ctx, qsb_track_stats* stats);
+/* the same call in two halves, for drivers that run exchange rounds between ranks in the middle (qsb_track, qsb_send_slab,
+ * qsb_put_arrivals ... until no rank sent anything): begin = qsb_cycle_begin + qsb_stream_begin on the host model's vaults,
+ * end = qsb_stream_end + balance + flux sum into the host model's tallies. */
+int  qsb_mc_tracking_begin(qsb_mc* mc, qsb_ctx* ctx);
+int  qsb_mc_tracking_end(qsb_mc* mc, qsb_ctx* ctx);
 
 const char* qsb_version(void);
 

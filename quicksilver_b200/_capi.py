@@ -103,6 +103,7 @@ def _declare(lib):
         "qsb_mc_get_double": (C.c_int, [vp, C.c_char_p, _P(C.c_double)]),
         "qsb_mc_cycle_init": (C.c_int, [vp]),
         "qsb_mc_processing": (C.c_int, [vp, _P(vp), u64p]),
+        "qsb_mc_processed": (C.c_int, [vp, _P(vp), u64p]),
         "qsb_mc_set_tracking_result": (C.c_int, [vp, vp, C.c_uint64, u64p, C.c_double]),
         "qsb_mc_cycle_finalize": (C.c_int, [vp, u64p, _P(C.c_double)]),
         "qsb_mc_cumulative_balance": (C.c_int, [vp, u64p]),
@@ -114,6 +115,10 @@ def _declare(lib):
         "qsb_cycle_begin": (C.c_int, [vp, C.c_int]),
         "qsb_put_particles": (C.c_int, [vp, vp, C.c_uint64]),
         "qsb_track": (C.c_int, [vp, _P(TrackStats)]),
+        "qsb_stream_begin": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64]),
+        "qsb_stream_end": (C.c_int, [vp, u64p]),
+        "qsb_get_census_range": (C.c_int, [vp, C.c_uint64, vp, C.c_uint64]),
+        "qsb_track_host": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, u64p, _P(TrackStats)]),
         "qsb_census_count": (C.c_int, [vp, u64p]),
         "qsb_get_census": (C.c_int, [vp, vp, C.c_uint64, u64p]),
         "qsb_get_balance": (C.c_int, [vp, u64p]),
@@ -128,6 +133,8 @@ def _declare(lib):
         "qsb_launch_count": (C.c_uint64, [vp]),
         "qsb_get_diagnostics": (C.c_int, [vp, u64p]),
         "qsb_mc_cycle_tracking": (C.c_int, [vp, vp, _P(TrackStats)]),
+        "qsb_mc_tracking_begin": (C.c_int, [vp, vp]),
+        "qsb_mc_tracking_end": (C.c_int, [vp, vp]),
     }
     missing = []
     for name, (res, args) in sig.items():

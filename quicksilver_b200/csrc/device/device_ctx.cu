@@ -165,6 +165,23 @@ struct qsb_ctx
     unsigned long long ready_prefix = 0;
     unsigned long long consumed = 0;         // slots fully processed by earlier qsb_track calls of this cycle
     unsigned long long pending_inflight = 0; // histories written from the host side since the last qsb_track
+    // host-buffer streaming (qsb_stream_begin / qsb_track / qsb_stream_end, see include/qsb.h)
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    cudaEvent_t ev_ctl = nullptr, ev_stage[2] = { nullptr, nullptr };
+    qsb_base_particle* d_in_aos = nullptr;      size_t in_aos_cap = 0;
+    qsb_base_particle* d_census_aos = nullptr;  // [vault capacity]
+    unsigned int* d_chunk_done = nullptr;       // [n_chunks]
+    unsigned int* h_chunk_flags = nullptr;      // [n_chunks] pinned + mapped
+    unsigned int* d_chunk_flags = nullptr;      // device alias of h_chunk_flags
+    unsigned long long* h_marks = nullptr;      // [n_marks] pinned: values copied into ctl->in_ready, one per input chunk
+    size_t n_marks = 0;
+    size_t n_chunks = 0;
+    bool streaming = false, stream_input_issued = false;
+    const qsb_base_particle* host_in = nullptr;
+    unsigned long long n_in_aos = 0;            // tickets [0, n_in_aos) are streamed host records this cycle
+    qsb_base_particle* host_out = nullptr;
+    unsigned long long host_out_cap = 0, census_copied = 0;   // records already on their way to host_out
+    size_t next_chunk = 0;
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
@@ -249,6 +266,11 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         QSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         QSB_CUDA(cudaEventCreate(&c->ev0));
         QSB_CUDA(cudaEventCreate(&c->ev1));
+        QSB_CUDA(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
+        QSB_CUDA(cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking));
+        QSB_CUDA(cudaEventCreateWithFlags(&c->ev_ctl, cudaEventDisableTiming));
+        QSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
+        QSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
 
         // ---- image ----
         const size_t nc = image->n_cells, ng = image->n_groups, nm = image->n_materials, mr = image->max_reactions_per_material;
@@ -294,6 +316,15 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
             im.dy = image->global_ly / image->global_ny;
             im.dz = image->global_lz / image->global_nz;
             im.margin = 1e-6 * std::min(im.dx, std::min(im.dy, im.dz));
+            {
+                // energy-group estimate (track_kernels.cu: energy_group): edges are e[i] ~ e[0] * (e[n-1]/e[0])^(i/(n)) up to
+                // the reference's spacing quirk; only an estimate, the kernel corrects it against the table
+                const double lo = std::log2(std::max(image->energies[0], 1e-300));
+                const double second = ng >= 2 ? std::log2(std::max(image->energies[1], 1e-300)) : lo + 1.0;
+                const double step = second > lo ? second - lo : 1.0;
+                im.group_log2_lo = (float)lo;
+                im.group_inv_dlog2 = (float)(1.0 / step);
+            }
             im.inv_hx = 2.0 / im.dx; im.inv_hy = 2.0 / im.dy; im.inv_hz = 2.0 / im.dz;
             std::vector<CellRec> recs(nc);
             bool compact = image->global_nx < 65535 && image->global_ny < 65535 && image->global_nz < 65535 && nm <= 255;
@@ -409,6 +440,12 @@ int qsb_destroy(qsb_ctx* c)
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_partial) cudaFreeHost(c->h_partial);
     if (c->h_staging) cudaFreeHost(c->h_staging);
+    if (c->h_chunk_flags) cudaFreeHost(c->h_chunk_flags);
+    if (c->h_marks) cudaFreeHost(c->h_marks);
+    if (c->stream_in) cudaStreamDestroy(c->stream_in);
+    if (c->stream_out) cudaStreamDestroy(c->stream_out);
+    if (c->ev_ctl) cudaEventDestroy(c->ev_ctl);
+    for (cudaEvent_t e : c->ev_stage) if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -423,6 +460,8 @@ int qsb_cycle_begin(qsb_ctx* c, int keep_census)
         unsigned long long carried = 0;
         if (keep_census && c->in_cycle)
         {
+            if (c->streaming)
+            { c->error = "keep_census: the census of a streamed cycle (qsb_stream_begin) was delivered to the host, not kept in the vault"; return (int)QSB_ERR_STATE; }
             pullControl(c);
             carried = std::min<unsigned long long>(c->h_ctl->census_count, c->vault[1 - c->proc].capacity);
             c->proc = 1 - c->proc;                           // last cycle's census becomes the processing vault
@@ -435,6 +474,8 @@ int qsb_cycle_begin(qsb_ctx* c, int keep_census)
         c->ready_prefix = carried;
         c->consumed = 0;
         c->pending_inflight = carried;
+        c->streaming = false; c->stream_input_issued = false;
+        c->n_in_aos = 0; c->host_in = nullptr; c->host_out = nullptr; c->host_out_cap = 0; c->census_copied = 0; c->next_chunk = 0;
         pushControl(c);
         QSB_CUDA(cudaMemsetAsync(c->flux, 0, (size_t)c->im.n_cells * c->im.n_groups * sizeof(double), c->stream));
         c->in_cycle = true;
@@ -447,6 +488,7 @@ int qsb_put_particles(qsb_ctx* c, const qsb_base_particle* aos, uint64_t n)
     if (n && !aos) return QSB_ERR_ARG;
     return guarded(c, [&]() {
         if (!c->in_cycle) { c->error = "qsb_put_particles before qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        if (c->streaming) { c->error = "qsb_put_particles after qsb_stream_begin: the cycle's input is the streamed host vault"; return (int)QSB_ERR_STATE; }
         VaultView& v = c->vault[c->proc];
         if (c->host_tail != c->h_ctl->tail)
         { c->error = "qsb_put_particles after tracking started: use qsb_put_arrivals"; return (int)QSB_ERR_STATE; }
@@ -483,16 +525,139 @@ int qsb_put_arrivals(qsb_ctx* c, const void* device_records, uint64_t n)
         if (n == 0) return (int)QSB_OK;
         pullControl(c);
         VaultView& v = c->vault[c->proc];
-        const unsigned long long first = c->h_ctl->tail;
+        const unsigned long long first = c->h_ctl->tail - c->n_in_aos;      // SoA slot: tickets below n_in_aos are streamed records
         if (first + n > v.capacity) { c->error = "processing vault capacity exceeded by arrivals"; return (int)QSB_ERR_CAPACITY; }
         const int grid = (int)std::min<uint64_t>((n + 255) / 256, 4096);
         arrivals_to_soa_kernel<<<grid, 256, 0, c->stream>>>((const ExchangeRecord*)device_records, n, v, first, c->d_domain_offset, c->epoch);
         c->launches++;
         QSB_CUDA(cudaGetLastError());
-        c->h_ctl->tail = first + n;
+        c->h_ctl->tail += n;
         c->pending_inflight += n;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         QSB_CUDA(cudaStreamSynchronize(c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+} // extern "C"
+
+namespace {
+
+constexpr unsigned kCensusChunkShift = 16;                       // 65 536 records = 8.9 MB per D2H copy
+constexpr size_t kInputChunkRecords = 1u << 16;                  // likewise for the H2D side
+
+bool isPinnedHost(const void* p)
+{
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// enqueue the H2D copies of the streamed host vault, chunk by chunk, each followed by an 8-byte copy that moves
+// ctl->in_ready forward (stream order: a chunk has landed before its mark).  Pinned source: everything is enqueued at
+// once and runs on the copy engine while the kernel tracks.  Pageable source: staged through the two halves of the
+// pinned bounce buffer by this thread, census chunks serviced in between.
+void serviceCensus(qsb_ctx* c, bool final);
+
+void issueStreamInput(qsb_ctx* c)
+{
+    if (c->stream_input_issued || c->n_in_aos == 0) { c->stream_input_issued = true; return; }
+    c->stream_input_issued = true;
+    const unsigned long long n = c->n_in_aos;
+    const size_t n_chunks = (n + kInputChunkRecords - 1) / kInputChunkRecords;
+    if (n_chunks > c->n_marks)
+    {
+        if (c->h_marks) cudaFreeHost(c->h_marks);
+        c->n_marks = n_chunks + 64;
+        QSB_CUDA(cudaMallocHost((void**)&c->h_marks, c->n_marks * sizeof(unsigned long long)));
+    }
+    const bool pinned = isPinnedHost(c->host_in);
+    const size_t half = c->staging_records / 2;
+    size_t k = 0;
+    for (unsigned long long done = 0; done < n; ++k)
+    {
+        const unsigned long long m = std::min<unsigned long long>(pinned ? kInputChunkRecords : std::min(kInputChunkRecords, half), n - done);
+        const void* src = c->host_in + done;
+        if (!pinned)
+        {
+            const int h = (int)(k & 1);
+            QSB_CUDA(cudaEventSynchronize(c->ev_stage[h]));             // this half's previous copy has left
+            char* bounce = (char*)c->h_staging + (size_t)h * half * sizeof(qsb_base_particle);
+            std::memcpy(bounce, src, m * sizeof(qsb_base_particle));
+            src = bounce;
+        }
+        QSB_CUDA(cudaMemcpyAsync(c->d_in_aos + done, src, m * sizeof(qsb_base_particle), cudaMemcpyHostToDevice, c->stream_in));
+        if (!pinned) QSB_CUDA(cudaEventRecord(c->ev_stage[k & 1], c->stream_in));
+        done += m;
+        if (k >= c->n_marks) throw CudaFailure{ "internal: input chunk marks exhausted" };
+        c->h_marks[k] = done;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->in_ready, &c->h_marks[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream_in));
+        if (!pinned) serviceCensus(c, false);
+    }
+}
+
+// start the D2H copy of every census chunk the kernel has announced (final = false), or of everything that is left
+// once the kernel has ended and the control block is back (final = true)
+void serviceCensus(qsb_ctx* c, bool final)
+{
+    if (!c->streaming || !c->host_out) return;
+    const unsigned long long chunk = 1ull << kCensusChunkShift;
+    while (c->next_chunk < c->n_chunks && *((volatile unsigned int*)&c->h_chunk_flags[c->next_chunk]) == c->epoch)
+    {
+        const unsigned long long first = (unsigned long long)c->next_chunk * chunk;
+        if (first + chunk > c->host_out_cap) break;                       // the caller's buffer ends here; the rest is fetched later
+        QSB_CUDA(cudaMemcpyAsync(c->host_out + first, c->d_census_aos + first, chunk * sizeof(qsb_base_particle),
+                                 cudaMemcpyDeviceToHost, c->stream_out));
+        c->census_copied = first + chunk;
+        c->next_chunk++;
+    }
+    if (final)
+    {
+        const unsigned long long n = std::min<unsigned long long>(std::min<unsigned long long>(c->h_ctl->census_count, c->vault[0].capacity), c->host_out_cap);
+        if (n > c->census_copied)
+        {
+            QSB_CUDA(cudaMemcpyAsync(c->host_out + c->census_copied, c->d_census_aos + c->census_copied,
+                                     (n - c->census_copied) * sizeof(qsb_base_particle), cudaMemcpyDeviceToHost, c->stream_out));
+            c->census_copied = n;
+            c->next_chunk = (size_t)(n >> kCensusChunkShift);
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int qsb_stream_begin(qsb_ctx* c, const qsb_base_particle* in, uint64_t n_in, qsb_base_particle* census_out, uint64_t census_cap)
+{
+    if ((n_in && !in) || (census_cap && !census_out)) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->in_cycle) { c->error = "qsb_stream_begin before qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        if (c->streaming || c->host_tail != c->ready_prefix || c->h_ctl->tail != c->host_tail)
+        { c->error = "qsb_stream_begin must directly follow qsb_cycle_begin"; return (int)QSB_ERR_STATE; }
+        const unsigned long long cap = c->vault[0].capacity;
+        if (n_in > c->in_aos_cap)
+        {
+            c->in_aos_cap = std::max<size_t>(n_in + n_in / 4, 1u << 20);
+            c->d_in_aos = devAlloc<qsb_base_particle>(c->in_aos_cap, c->owned);      // the previous, smaller one stays owned until destroy
+        }
+        if (!c->d_census_aos)
+        {
+            c->d_census_aos = devAlloc<qsb_base_particle>(cap, c->owned);
+            c->n_chunks = (size_t)((cap + (1ull << kCensusChunkShift) - 1) >> kCensusChunkShift);
+            c->d_chunk_done = devAlloc<unsigned int>(c->n_chunks, c->owned);
+            QSB_CUDA(cudaHostAlloc((void**)&c->h_chunk_flags, c->n_chunks * sizeof(unsigned int), cudaHostAllocMapped));
+            std::memset(c->h_chunk_flags, 0, c->n_chunks * sizeof(unsigned int));
+            QSB_CUDA(cudaHostGetDevicePointer((void**)&c->d_chunk_flags, c->h_chunk_flags, 0));
+        }
+        QSB_CUDA(cudaMemsetAsync(c->d_chunk_done, 0, c->n_chunks * sizeof(unsigned int), c->stream));
+        c->streaming = true; c->stream_input_issued = false;
+        c->host_in = in; c->n_in_aos = n_in;
+        c->host_out = census_out; c->host_out_cap = census_cap; c->census_copied = 0; c->next_chunk = 0;
+        c->h_ctl->tail += n_in;                       // ticket space: [0, n_in) streamed records, then the SoA slots
+        c->host_tail = c->h_ctl->tail;
+        c->pending_inflight += n_in;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         return (int)QSB_OK;
     });
 }
@@ -507,7 +672,11 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.census = c->vault[1 - c->proc];
         a.sends = c->sends; a.send_capacity = c->send_capacity;
         a.ctl = c->d_ctl; a.flux = c->flux; a.dt = c->dt; a.ready_prefix = c->ready_prefix;
-        a.epoch = c->epoch; a.check_geometry = (c->opt.tracking_mode & 2) ? 1 : 0;
+        a.epoch = c->epoch;
+        a.check_mode = ((c->opt.tracking_mode & 2) ? 1 : 0) | ((c->opt.tracking_mode & 4) ? 2 : 0);
+        a.in_aos = c->d_in_aos; a.n_in = c->n_in_aos;
+        a.census_aos = c->streaming ? c->d_census_aos : nullptr;
+        a.census_chunk_done = c->d_chunk_done; a.host_chunk_flags = c->d_chunk_flags; a.census_chunk_shift = kCensusChunkShift;
         uint32_t n_launch = 0;
         // tickets handed out past the tail by the previous call were never redeemed: restart at the consumed mark
         c->h_ctl->head = c->consumed;
@@ -515,6 +684,12 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         c->pending_inflight = 0;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->head, &c->h_ctl->head, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->inflight, &c->h_ctl->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        if (c->streaming && !c->stream_input_issued)
+        {
+            // the DMA front must not start moving ctl->in_ready before the control block of this cycle is in place
+            QSB_CUDA(cudaEventRecord(c->ev_ctl, c->stream));
+            QSB_CUDA(cudaStreamWaitEvent(c->stream_in, c->ev_ctl, 0));
+        }
         QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
         if (c->h_ctl->inflight > 0)
         {
@@ -524,13 +699,19 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             ++n_launch; c->launches++;
         }
         QSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        if (c->streaming)
+        {
+            issueStreamInput(c);                                    // H2D of the host vault runs under the kernel
+            while (cudaEventQuery(c->ev1) == cudaErrorNotReady) serviceCensus(c, false);   // D2H of finished census chunks too
+            QSB_CUDA(cudaGetLastError());
+        }
         pullControl(c);
         QSB_CUDA(cudaEventSynchronize(c->ev1));
         float ms = 0;
         QSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         if (c->h_ctl->inflight != 0 && !c->h_ctl->overflow)
         { c->error = "tracking kernel ended with histories in flight"; return (int)QSB_ERR_INTERNAL; }
-        c->consumed = std::min<unsigned long long>(c->h_ctl->tail, a.proc.capacity);
+        c->consumed = std::min<unsigned long long>(c->h_ctl->tail, c->n_in_aos + a.proc.capacity);
         if (stats)
         {
             stats->n_processed = c->consumed;
@@ -553,6 +734,48 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         { c->error = "a collision selected no reaction (cross-section table inconsistent)"; return (int)QSB_ERR_INTERNAL; }
         return (int)QSB_OK;
     });
+}
+
+int qsb_stream_end(qsb_ctx* c, uint64_t* n_census)
+{
+    if (!n_census) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->streaming) { c->error = "qsb_stream_end without qsb_stream_begin"; return (int)QSB_ERR_STATE; }
+        pullControl(c);
+        *n_census = c->h_ctl->census_count;
+        serviceCensus(c, true);
+        QSB_CUDA(cudaStreamSynchronize(c->stream_out));
+        QSB_CUDA(cudaStreamSynchronize(c->stream_in));
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_get_census_range(qsb_ctx* c, uint64_t first, qsb_base_particle* out, uint64_t count)
+{
+    if (count && !out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->streaming) { c->error = "qsb_get_census_range: the census of this cycle is not in record (streamed) form"; return (int)QSB_ERR_STATE; }
+        pullControl(c);
+        if (first + count > c->h_ctl->census_count) { c->error = "census range out of bounds"; return (int)QSB_ERR_ARG; }
+        if (count == 0) return (int)QSB_OK;
+        if (isPinnedHost(out))
+        {
+            QSB_CUDA(cudaMemcpyAsync(out, c->d_census_aos + first, count * sizeof(qsb_base_particle), cudaMemcpyDeviceToHost, c->stream_out));
+            QSB_CUDA(cudaStreamSynchronize(c->stream_out));
+        }
+        else QSB_CUDA(cudaMemcpy(out, c->d_census_aos + first, count * sizeof(qsb_base_particle), cudaMemcpyDeviceToHost));
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_track_host(qsb_ctx* c, const qsb_base_particle* in, uint64_t n_in, qsb_base_particle* census_out, uint64_t census_cap,
+                   uint64_t* n_census, qsb_track_stats* stats)
+{
+    int rc = qsb_stream_begin(c, in, n_in, census_out, census_cap);
+    if (rc != QSB_OK) return rc;
+    rc = qsb_track(c, stats);
+    if (rc != QSB_OK) return rc;
+    return qsb_stream_end(c, n_census);
 }
 
 int qsb_get_diagnostics(qsb_ctx* c, uint64_t out[8])
@@ -581,6 +804,12 @@ int qsb_get_census(qsb_ctx* c, qsb_base_particle* aos, uint64_t cap, uint64_t* n
         const uint64_t n = c->h_ctl->census_count;
         *n_out = n;
         if (n > cap || (n && !aos)) { c->error = "census buffer too small"; return (int)QSB_ERR_CAPACITY; }
+        if (c->streaming)
+        {
+            // this cycle's census was written in record form (qsb_stream_begin): one plain copy
+            if (n) QSB_CUDA(cudaMemcpy(aos, c->d_census_aos, n * sizeof(qsb_base_particle), cudaMemcpyDeviceToHost));
+            return (int)QSB_OK;
+        }
         const VaultView& v = c->vault[1 - c->proc];
         const size_t chunk = c->staging_records;
         for (uint64_t done = 0; done < n; done += chunk)

@@ -35,6 +35,7 @@ struct DevImage
     double dx, dy, dz;              // cell size (global_l / global_n, the host grid's own expression)
     double margin;                  // robustness margin of the fast geometry path: 1e-6 * smallest cell edge
     double inv_hx, inv_hy, inv_hz;  // 2/dx, 2/dy, 2/dz (filter arithmetic only)
+    float group_log2_lo, group_inv_dlog2; // energy-group index estimate: (log2(E) - log2_lo) * inv_dlog2 (estimate only)
     const CellRec* cells;           // [n_cells]
     const double2* xs_pair;         // [n_materials*n_groups] {total, 1/total}
     const double4* planes;          // [n_cells*24] {A,B,C,D}, 32-byte aligned records
@@ -89,6 +90,7 @@ struct DevControl
     unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];
     unsigned long long n_lookups;       // diagnostics
+    unsigned long long in_ready;        // host-buffer streaming: input records [0, in_ready) have landed in HBM
     unsigned int overflow;              // bit0 processing vault, bit1 census vault, bit2 send slab
     unsigned int bad_reaction;          // collisions where no reaction was selected (reference: unreachable)
     unsigned int epoch;
@@ -106,9 +108,19 @@ struct TrackArgs
     DevControl* ctl;
     double* flux;                       // [n_cells][n_groups]
     double dt;
-    unsigned long long ready_prefix;    // slots below this index were written by the host side
+    unsigned long long ready_prefix;    // SoA slots below this index were written by the host side
+    // host-buffer streaming (qsb_track_host): the first n_in tickets are AoS records of the host vault, DMA-copied chunk by
+    // chunk into in_aos while the kernel runs (ctl->in_ready says how far); SoA slot = ticket - n_in for the rest.  Census
+    // records are written as AoS into census_aos; every full chunk of 2^census_chunk_shift records is announced to the host
+    // through a flag in mapped pinned memory so that its D2H copy overlaps the tracking still going on.
+    const qsb_base_particle* in_aos;
+    unsigned long long n_in;
+    qsb_base_particle* census_aos;      // nullptr: census goes to the SoA vault
+    unsigned int* census_chunk_done;    // [chunks] records completed per chunk (device memory)
+    unsigned int* host_chunk_flags;     // [chunks] mapped pinned host memory: == epoch once the chunk is complete
+    unsigned int census_chunk_shift;
     uint32_t epoch;                     // value of a slot's ready word once it is fully written this cycle
-    int check_geometry;                 // 1: evaluate both geometry paths and count disagreements
+    int check_mode;                     // bit 0: evaluate both geometry paths, bit 1: both reaction selections; count disagreements
 };
 
 // launchers implemented twice in track_kernels.cu (validation: --fmad=false + strict math; fast)

@@ -48,6 +48,11 @@ constexpr double kSmallDouble = 1.0e-10;
 constexpr double kHugeDouble = 1.0e+75;
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr unsigned long long kNoTicket = ~0ull;
+#ifndef QSB_REFILL
+#define QSB_REFILL 8
+#endif
+constexpr unsigned kRefill = QSB_REFILL;  // idle lanes a warp lets gather before it runs its service phase
+constexpr unsigned kTicketBatch = 32;     // tickets a warp reserves per atomicAdd on the queue head
 
 // facet -> 3 of the cell's 14 points, and facet -> matching facet of the face neighbour (src/MC_Domain.cc:41-50)
 __constant__ int8_t c_facet_points[24][4] = {
@@ -92,38 +97,28 @@ __device__ __forceinline__ uint4 load_cell_head(const DevImage& im, int cell)
     return __ldg(reinterpret_cast<const uint4*>(im.cells + cell));
 }
 
-__device__ __forceinline__ double m_log(double x)
-{
-#if QSB_VALIDATION
-    return qs_strict_log(x);
-#else
-    return log(x);
-#endif
-}
+// log / sin / cos: the portable functions of qs_strict_math.h in BOTH builds.  Validation (--fmad=false) gets the bits
+// of the CPU oracle; the fast build contracts them to FMAs (same ~1 ulp accuracy) and avoids the CUDA math library's
+// out-of-line argument-reduction slow path, which the tracking loop can never reach (0 <= phi < 2 pi, 0 < r < 1).
+__device__ __forceinline__ double m_log(double x) { return qs_strict_log(x); }
+__device__ __forceinline__ void m_sincos(double phi, double* s, double* c) { qs_strict_sincos(phi, s, c); }
 
-__device__ __forceinline__ void m_sincos(double phi, double* s, double* c)
-{
-#if QSB_VALIDATION
-    qs_strict_sincos(phi, s, c);
-#else
-    sincos(phi, s, c);
-#endif
-}
-
-// src/NuclearData.cc:208-227
+// src/NuclearData.cc:208-227.  The reference bisects the nGroups+1 edges: for e[0] < energy <= e[n-1] it returns the
+// largest i <= n-2 with e[i] <= energy.  The edges are log-spaced (src/NuclearData.cc:105-119), so the index is first
+// estimated from a single-precision log2 and then corrected against the table itself -- the answer is decided by
+// the same comparisons on the same doubles, so it is the reference's for ANY increasing table; a bad estimate only costs
+// extra steps.  Two dependent loads instead of eight.
 __device__ __forceinline__ int energy_group(const DevImage& im, double energy)
 {
     const int n = im.n_groups + 1;
     const double* __restrict__ e = im.energies;
     if (energy <= __ldg(e)) return 0;
     if (energy > __ldg(e + n - 1)) return n - 1;
-    int high = n - 1, low = 0;
-    while (high != low + 1)
-    {
-        const int mid = (high + low) / 2;
-        if (energy < __ldg(e + mid)) high = mid; else low = mid;
-    }
-    return low;
+    int i = (int)((__log2f((float)energy) - im.group_log2_lo) * im.group_inv_dlog2);
+    i = min(max(i, 0), n - 2);
+    while (i > 0 && energy < __ldg(e + i)) --i;
+    while (i < n - 2 && energy >= __ldg(e + i + 1)) ++i;
+    return i;
 }
 
 __device__ __forceinline__ double speed_of(const Particle& p) { return sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz); }
@@ -158,6 +153,27 @@ __device__ __forceinline__ void load_particle(const TrackArgs& a, unsigned long 
     p.facet = 0; p.total_xs = 0.0;
     p.head = load_cell_head(a.im, p.cell);
     reload_transform(a.im, p, a.dt, p.alpha != p.alpha);
+}
+
+// host-buffer streaming: ticket i is record i of the host vault, DMA-copied into HBM as it is (136-byte
+// MC_Base_Particle layout, src/MC_Base_Particle.hh:75-92).  Read once per history with 17 L2 (.cg) loads.
+__device__ __forceinline__ void load_particle_aos(const TrackArgs& a, unsigned long long i, Particle& p)
+{
+    const double* __restrict__ r = reinterpret_cast<const double*>(a.in_aos + i);
+    p.x = __ldcg(r + 0); p.y = __ldcg(r + 1); p.z = __ldcg(r + 2);
+    p.vx = __ldcg(r + 3); p.vy = __ldcg(r + 4); p.vz = __ldcg(r + 5);
+    p.energy = __ldcg(r + 6); p.weight = __ldcg(r + 7); p.ttc = __ldcg(r + 8);
+    p.age = __ldcg(r + 9); p.nmfp = __ldcg(r + 10); p.nseg = __ldcg(r + 11);
+    const unsigned long long* __restrict__ u = reinterpret_cast<const unsigned long long*>(r);
+    p.seed = (uint64_t)__ldcg(u + 12); p.id = (uint64_t)__ldcg(u + 13);
+    const unsigned long long t0 = __ldcg(u + 14), t1 = __ldcg(u + 15), t2 = __ldcg(u + 16);
+    p.last_event = (int)(unsigned)t0; p.num_collisions = (int)(unsigned)(t0 >> 32);
+    p.breed = (int)(unsigned)t1; p.species = (int)(unsigned)(t1 >> 32);
+    const int domain = (int)(unsigned)t2, cell = (int)(unsigned)(t2 >> 32);
+    p.cell = __ldg(a.im.domain_cell_offset + domain) + cell;
+    p.facet = 0; p.total_xs = 0.0;
+    p.head = load_cell_head(a.im, p.cell);
+    reload_transform(a.im, p, a.dt, true);
 }
 
 __device__ __forceinline__ void store_particle(const VaultView& v, unsigned long long i, const Particle& p, bool with_direction)
@@ -374,7 +390,7 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
 
     int nf_facet = 0; double d_facet = 0.0;
     const bool fast = im.compact && nearest_facet_fast(im, p, nf_facet, d_facet);
-    if (!fast || (a.check_geometry != 0))
+    if (!fast || (a.check_mode & 1))
     {
         int f2; double d2;
         double qx = p.x, qy = p.y, qz = p.z;
@@ -447,21 +463,23 @@ __device__ __forceinline__ void update_trajectory(double energy, double angle, P
 // append a secondary to the processing vault: count it in flight, write it, then publish the slot
 __device__ __forceinline__ void push_secondary(const TrackArgs& a, const Particle& child, uint32_t epoch)
 {
-    const unsigned long long slot = atomicAdd(&a.ctl->tail, 1ull);
+    const unsigned long long slot = atomicAdd(&a.ctl->tail, 1ull) - a.n_in;     // tickets below n_in are the streamed host records
     if (slot >= a.proc.capacity) { atomicOr(&a.ctl->overflow, 1u); return; }
     atomicAdd(&a.ctl->inflight, 1ull);
     store_particle(a.proc, slot, child, false);
-    __threadfence();
-    *((volatile uint32_t*)(a.proc.ready + slot)) = epoch;
+    // publish: release store (MEMBAR.ALL.GPU + STG, no L1 invalidation -- __threadfence() would add CCTL.IVALL and
+    // throw away this SM's cached cell records and cross-section tables on every fission)
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.proc.ready + slot), "r"(epoch) : "memory");
 }
 
 // The reference walks the material's (isotope, reaction) table subtracting each macroscopic cross section until
 // the running value goes negative (src/CollisionEvent.cc:59-83).  Every isotope of a material carries the same
 // reaction table (src/initMC.cc:160-196; checked per material on the host), so the NR per-reaction values are
-// held in registers and the same subtraction chain runs without further loads.  Returns the flat index
-// iso * n_react + react, or -1.
+// held in registers.  Returns the flat index iso * n_react + react, or -1.
+//
+// exact chain: the reference's own sequence of subtractions, isotope after isotope.
 template <int NR>
-__device__ __forceinline__ int select_reaction_periodic(const double* __restrict__ table, int n_iso, int n_react, double current)
+__device__ __noinline__ int select_reaction_chain(const double* __restrict__ table, int n_iso, int n_react, double current)
 {
     double v[NR];
 #pragma unroll
@@ -485,6 +503,50 @@ __device__ __forceinline__ int select_reaction_periodic(const double* __restrict
     return -1;
 }
 
+// filtered exact selection: the chain value after k subtractions differs from (current - prefix sum) by at most
+// k roundings of at most ulp(total)/2 each, i.e. by less than 180 * 2^-53 * total ~ 2e-14 * total.  The entry the chain
+// selects is therefore the first k with current < prefix[k+1] whenever `current` keeps a distance of `guard`
+// = 1e-11 * total from the two prefix sums around it -- which is decided here with one division instead of
+// walking up to n_iso * NR dependent subtractions.  Inside the guard band (probability ~1e-9 per collision) or when
+// the estimate falls outside the table, the exact chain decides.  tracking_mode bit 2 runs both and counts
+// disagreements (tests require 0).
+template <int NR>
+__device__ __forceinline__ int select_reaction_periodic(const double* __restrict__ table, int n_iso, int n_react, double current,
+                                                        double total, bool check, unsigned int& mismatch)
+{
+    double prefix[NR];
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { sum += (k < n_react) ? __ldg(table + k) : 0.0; prefix[k] = sum; }
+    const double guard = 1e-11 * total;
+    int selected = -2;
+    if (sum > 0.0)
+    {
+        const int iso = (int)(current / sum);
+        const double rest = current - (double)iso * sum;          // position inside isotope `iso`, up to a few ulp(total)
+        if (iso < n_iso && rest > guard)
+        {
+            int first = -1;
+            double below = 0.0, above = 0.0;
+#pragma unroll
+            for (int k = 0; k < NR; ++k)
+            {
+                if (first < 0 && k < n_react)
+                {
+                    if (rest < prefix[k]) { first = k; above = prefix[k]; }
+                    else below = prefix[k];
+                }
+            }
+            // `first` is the first entry whose prefix sum exceeds rest (a zero-width entry, cross section 0, is skipped
+            // exactly as the chain skips it); accepted when rest sits clear of both neighbouring prefix sums
+            if (first >= 0 && above - rest > guard && rest - below > guard) selected = iso * n_react + first;
+        }
+    }
+    if (selected == -2) return select_reaction_chain<NR>(table, n_iso, n_react, current);
+    if (check && select_reaction_chain<NR>(table, n_iso, n_react, current) != selected) mismatch++;
+    return selected;
+}
+
 __device__ __forceinline__ int select_reaction_generic(const double* __restrict__ table, int n_total, double current)
 {
     for (int k = 0; k < n_total; ++k)
@@ -506,9 +568,11 @@ __device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p,
     double r = qs_rng_sample(&p.seed);
     const double current = p.total_xs * r;
     int selected;
-    if (__ldg(im.mat_periodic + mat) && n_react <= 3)      selected = select_reaction_periodic<3>(table, n_iso, n_react, current);
-    else if (__ldg(im.mat_periodic + mat) && n_react <= 9) selected = select_reaction_periodic<9>(table, n_iso, n_react, current);
-    else                                                   selected = select_reaction_generic(table, n_iso * n_react, current);
+    const bool periodic = __ldg(im.mat_periodic + mat) != 0;
+    const bool check = (a.check_mode & 2) != 0;
+    if (periodic && n_react <= 3)      selected = select_reaction_periodic<3>(table, n_iso, n_react, current, p.total_xs, check, c.mismatch);
+    else if (periodic && n_react <= 9) selected = select_reaction_periodic<9>(table, n_iso, n_react, current, p.total_xs, check, c.mismatch);
+    else                               selected = select_reaction_generic(table, n_iso * n_react, current);
     c.lookups += (selected < 0 ? n_iso * n_react : selected + 1);
     if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return false; }
 
@@ -650,67 +714,164 @@ __device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particl
     return false;
 }
 
-__device__ __forceinline__ void census_event(const TrackArgs& a, const Particle& p, Counters& c)
+// census record as the host wants it: MC_Base_Particle layout, 17 eight-byte L2 stores
+__device__ __forceinline__ void store_census_aos(const DevImage& im, qsb_base_particle* rec, const Particle& p)
 {
-    const unsigned long long slot = atomicAdd(&a.ctl->census_count, 1ull);
-    c.census++;
-    if (slot >= a.census.capacity) { atomicOr(&a.ctl->overflow, 2u); return; }
-    store_particle(a.census, slot, p, false);
+    double* r = reinterpret_cast<double*>(rec);
+    __stcg(r + 0, p.x); __stcg(r + 1, p.y); __stcg(r + 2, p.z);
+    __stcg(r + 3, p.vx); __stcg(r + 4, p.vy); __stcg(r + 5, p.vz);
+    __stcg(r + 6, p.energy); __stcg(r + 7, p.weight); __stcg(r + 8, p.ttc);
+    __stcg(r + 9, p.age); __stcg(r + 10, p.nmfp); __stcg(r + 11, p.nseg);
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(rec);
+    __stcg(u + 12, (unsigned long long)p.seed); __stcg(u + 13, (unsigned long long)p.id);
+    const int d = flat_to_domain(im, p.cell);
+    const int local = p.cell - __ldg(im.domain_cell_offset + d);
+    __stcg(u + 14, (unsigned long long)(unsigned)p.last_event | ((unsigned long long)(unsigned)p.num_collisions << 32));
+    __stcg(u + 15, (unsigned long long)(unsigned)p.breed | ((unsigned long long)(unsigned)p.species << 32));
+    __stcg(u + 16, (unsigned long long)(unsigned)d | ((unsigned long long)(unsigned)local << 32));
+}
+
+// Census append, executed in the warp's service phase by all lanes whose history ended at census since the last
+// service phase (`pending`), converged: one atomic for the group, one record per lane -- SoA vault, or the record-form
+// buffer when the census is being streamed to the host.
+__device__ __forceinline__ void census_flush(const TrackArgs& a, const Particle& p, bool pending, unsigned lane)
+{
+    const unsigned group = __ballot_sync(kFullMask, pending);
+    if (group == 0u) return;
+    const int leader = __ffs(group) - 1;
+    const unsigned n = __popc(group);
+    unsigned long long base = 0;
+    if ((int)lane == leader) base = atomicAdd(&a.ctl->census_count, (unsigned long long)n);
+    base = __shfl_sync(kFullMask, base, leader);
+    if (pending)
+    {
+        const unsigned long long slot = base + __popc(group & ((1u << lane) - 1u));
+        if (slot >= a.census.capacity) atomicOr(&a.ctl->overflow, 2u);
+        else if (a.census_aos) store_census_aos(a.im, a.census_aos + slot, p);
+        else store_particle(a.census, slot, p, false);
+    }
+    if (!a.census_aos) return;
+    // streaming: count the group's records into their chunk(s) with release semantics -- the records of the whole
+    // group (same warp, ordered by the __syncwarp) are visible before the count -- and tell the host about every chunk
+    // that became complete, through mapped pinned memory; its D2H copy then runs while tracking continues
+    __syncwarp();
+    if ((int)lane == leader)
+    {
+        const unsigned long long last = min(base + n, a.census.capacity);
+        unsigned long long at = base;
+        while (at < last)
+        {
+            const unsigned long long chunk = at >> a.census_chunk_shift;
+            const unsigned long long chunk_end = min((chunk + 1) << a.census_chunk_shift, last);
+            const unsigned cnt = (unsigned)(chunk_end - at);
+            unsigned old;
+            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.census_chunk_done + chunk), "r"(cnt) : "memory");
+            if (old + cnt == (1u << a.census_chunk_shift))
+                asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.host_chunk_flags + chunk), "r"(a.epoch) : "memory");
+            at = chunk_end;
+        }
+    }
 }
 
 __device__ __forceinline__ unsigned int warp_sum(unsigned int v) { return __reduce_add_sync(kFullMask, v); }
 
 // ---- the persistent history kernel ---------------------------------------------------------------------
 template <int kDummy>
-__global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ TrackArgs a)
+#ifndef QSB_MIN_BLOCKS
+#define QSB_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid_constant__ TrackArgs a)
 {
     const unsigned lane = threadIdx.x & 31u;
     Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     Particle p;
     bool have = false;
     unsigned long long ticket = kNoTicket;
+    unsigned long long pool_next = 0, pool_end = 0;     // warp-uniform: tickets reserved by this warp, not yet handed to a lane
+    unsigned long long in_seen = 0;                     // last value of ctl->in_ready this lane has seen
     const uint32_t epoch = a.epoch;
     unsigned backoff = 64;
+
+    bool census_pending = false;                        // history ended at census; the record is still in this lane's registers
 
     for (;;)
     {
         __syncwarp();
-        // 1. every idle lane without a ticket takes the next one: one atomicAdd per warp
-        const bool want = !have && ticket == kNoTicket;
-        const unsigned want_mask = __ballot_sync(kFullMask, want);
-        if (want_mask)
+        // SERVICE PHASE.  Ending a history (census store) and starting one (ticket, particle load, reload transform, energy
+        // group) are long code paths that single lanes reach at random times; run per lane as they come they would each cost
+        // the warp a full pass with one or two lanes active (measured: a third of all issue slots).  Idle lanes therefore wait
+        // until kRefill of them have gathered (or nothing is left to track) and then do it together, converged.
+        const unsigned idle_mask = __ballot_sync(kFullMask, !have);
+        if (__popc(idle_mask) >= kRefill || idle_mask == kFullMask)
         {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&a.ctl->head, (unsigned long long)__popc(want_mask));
-            base = __shfl_sync(kFullMask, base, 0);
-            if (want) ticket = base + __popc(want_mask & ((1u << lane) - 1u));
-        }
-        // 2. redeem: the slot is ready if the host wrote it (below ready_prefix) or its ready word carries this epoch
-        if (!have && ticket != kNoTicket && ticket < a.proc.capacity)
-        {
-            bool ready = ticket < a.ready_prefix;
-            if (!ready) ready = *((volatile uint32_t*)(a.proc.ready + ticket)) == epoch;
+            census_flush(a, p, census_pending, lane);
+            census_pending = false;
+
+            // 1. every idle lane without a ticket takes one from the warp's pool; the pool is refilled kTicketBatch tickets at a
+            //    time with a single atomicAdd (a reserved ticket is an obligation: it is always handed to a lane eventually)
+            const bool want = !have && ticket == kNoTicket;
+            const unsigned want_mask = __ballot_sync(kFullMask, want);
+            if (want_mask)
+            {
+                const unsigned long long avail = pool_end - pool_next;
+                const unsigned n_want = __popc(want_mask);
+                unsigned long long fresh = 0;
+                if (n_want > avail)
+                {
+                    if (lane == 0) fresh = atomicAdd(&a.ctl->head, (unsigned long long)kTicketBatch);
+                    fresh = __shfl_sync(kFullMask, fresh, 0);
+                }
+                const unsigned rank = __popc(want_mask & ((1u << lane) - 1u));
+                if (want) ticket = rank < avail ? pool_next + rank : fresh + (rank - avail);
+                if (n_want > avail) { pool_next = fresh + (n_want - avail); pool_end = fresh + kTicketBatch; }
+                else pool_next += n_want;
+            }
+            // 2. redeem.  A streamed host record is there once the DMA front (ctl->in_ready) has passed it; a vault slot is ready
+            //    if the host wrote it (below ready_prefix) or its ready word carries this epoch.  The flag is read with a relaxed
+            //    gpu-scope load and the particle with L2 (.cg) loads that depend on the branch: the data loads are not issued
+            //    before the flag value has come back, and the writer released the flag after the data, so no fence (and no L1
+            //    invalidation) is needed on this side.
+            bool ready = false;
+            if (!have && ticket != kNoTicket)
+            {
+                if (ticket < a.n_in)
+                {
+                    if (ticket >= in_seen)
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(in_seen) : "l"(&a.ctl->in_ready) : "memory");
+                    ready = ticket < in_seen;
+                }
+                else if (ticket - a.n_in < a.proc.capacity)
+                {
+                    const unsigned long long slot = ticket - a.n_in;
+                    ready = slot < a.ready_prefix;
+                    if (!ready)
+                    {
+                        uint32_t flag;
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + slot) : "memory");
+                        ready = flag == epoch;
+                    }
+                }
+            }
             if (ready)
             {
-                __threadfence();
-                load_particle(a, ticket, p);
+                if (ticket < a.n_in) load_particle_aos(a, ticket, p);
+                else load_particle(a, ticket - a.n_in, p);
                 have = true;
                 ticket = kNoTicket;
             }
+            if (__ballot_sync(kFullMask, have) == 0u)
+            {
+                // idle warp: the cycle is over when no history is queued or running anywhere on this GPU
+                unsigned long long inflight = 1;
+                if (lane == 0) inflight = *((volatile unsigned long long*)&a.ctl->inflight);
+                inflight = __shfl_sync(kFullMask, inflight, 0);
+                if (inflight == 0ull) break;
+                __nanosleep(backoff);
+                if (backoff < 2048) backoff *= 2;
+                continue;
+            }
+            backoff = 64;
         }
-        const unsigned have_mask = __ballot_sync(kFullMask, have);
-        if (have_mask == 0u)
-        {
-            // idle warp: the cycle is over when no history is queued or running anywhere on this GPU
-            unsigned long long inflight = 1;
-            if (lane == 0) inflight = *((volatile unsigned long long*)&a.ctl->inflight);
-            inflight = __shfl_sync(kFullMask, inflight, 0);
-            if (inflight == 0ull) break;
-            __nanosleep(backoff);
-            if (backoff < 2048) backoff *= 2;
-            continue;
-        }
-        backoff = 64;
 
         bool finished = false;
         if (have)
@@ -721,7 +882,7 @@ __global__ void __launch_bounds__(128, 3) track_kernel(const __grid_constant__ T
             bool keep;
             if (outcome == 0) keep = collision_event(a, p, c, epoch);
             else if (outcome == 1) keep = facet_crossing_event(a, p, c);
-            else { census_event(a, p, c); keep = false; }
+            else { census_pending = true; c.census++; keep = false; }     // stored in the next service phase
             have = keep;
             finished = !keep;
         }

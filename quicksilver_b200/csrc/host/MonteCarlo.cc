@@ -7,7 +7,50 @@
 
 #include "../qs_rng.h"
 
+#include <cuda_runtime_api.h>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_set>
+
 namespace qsb {
+
+// ---- vault storage: page-locked when a CUDA driver is present (see MonteCarlo.hh) ------------------------------
+namespace {
+std::mutex g_vaultMutex;
+std::unordered_set<void*> g_pinnedBlocks;
+}
+
+void* vaultAllocate(size_t bytes)
+{
+    if (bytes == 0) bytes = 1;
+    static const bool noPin = std::getenv("QSB_NO_PINNED_VAULTS") != nullptr;
+    if (!noPin)
+    {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess && p)
+        {
+            std::lock_guard<std::mutex> lock(g_vaultMutex);
+            g_pinnedBlocks.insert(p);
+            return p;
+        }
+        cudaGetLastError();      // no driver / no device / out of lockable memory: ordinary memory is fine
+    }
+    void* p = std::malloc(bytes);
+    if (!p) throw std::bad_alloc();
+    return p;
+}
+
+void vaultFree(void* p)
+{
+    if (!p) return;
+    bool pinned = false;
+    {
+        std::lock_guard<std::mutex> lock(g_vaultMutex);
+        pinned = g_pinnedBlocks.erase(p) != 0;
+    }
+    if (pinned) cudaFreeHost(p); else std::free(p);
+}
+
 
 MonteCarlo::MonteCarlo(const Parameters& p, int rank_, int nRanks_)
 : params(p), rank(rank_), nRanks(nRanks_),

@@ -6,7 +6,9 @@
 #define QSB_MONTECARLO_HH
 
 #include <cstdint>
+#include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../../include/qsb.h"
@@ -19,7 +21,28 @@ namespace qsb {
 // Host-side particle vault: one contiguous AoS of MC_Base_Particle-layout records.  The reference's
 // fixed-size batches (src/ParticleVaultContainer.hh) exist only to bound kernel launches and carry no
 // physics; tallies do not depend on vault order.
-typedef std::vector<qsb_base_particle> ParticleVault;
+//
+// Storage is page-locked (cudaHostAlloc) whenever a CUDA driver is present, so that the drop-in call
+// qsb_mc_cycle_tracking can stream the vault to the GPU and the census back with plain DMA, overlapped with
+// tracking, instead of staging through bounce buffers; on a machine without a GPU it is ordinary heap memory.
+// Elements are default-initialised (no zero fill on resize: the census is written by the device).
+void* vaultAllocate(size_t bytes);
+void  vaultFree(void* p);
+
+template <typename T>
+struct VaultAllocator
+{
+    typedef T value_type;
+    VaultAllocator() = default;
+    template <typename U> VaultAllocator(const VaultAllocator<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(vaultAllocate(n * sizeof(T))); }
+    void deallocate(T* p, size_t) { vaultFree(p); }
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+    template <typename U> bool operator==(const VaultAllocator<U>&) const { return true; }
+    template <typename U> bool operator!=(const VaultAllocator<U>&) const { return false; }
+};
+typedef std::vector<qsb_base_particle, VaultAllocator<qsb_base_particle>> ParticleVault;
 
 struct Balance
 {

@@ -145,6 +145,12 @@ int qsb_mc_processing(qsb_mc* h, const qsb_base_particle** aos, uint64_t* n)
     return guarded(h, [&](MonteCarlo& mc) { *aos = mc.processing.data(); *n = mc.processing.size(); return QSB_OK; });
 }
 
+int qsb_mc_processed(qsb_mc* h, const qsb_base_particle** aos, uint64_t* n)
+{
+    if (!aos) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) { *aos = mc.processed.data(); if (n) *n = mc.processed.size(); return QSB_OK; });
+}
+
 int qsb_mc_set_tracking_result(qsb_mc* h, const qsb_base_particle* census, uint64_t n_census,
                                const uint64_t balance[QSB_BAL_COUNT], double scalar_flux_sum)
 {
@@ -210,25 +216,66 @@ int qsb_mc_format_cycle_row(qsb_mc* h, int cycle, const uint64_t row[QSB_BAL_COU
 
 } // extern "C"
 
-// Drop-in for the reference's cycleTracking(MonteCarlo*) (src/main.cc:138-307) on one rank, written
-// purely against the device C ABI: host vault in, census + tallies out, copies included.
-extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* stats)
+// Drop-in for the reference's cycleTracking(MonteCarlo*) (src/main.cc:138-307), written purely against the device
+// C ABI: host vault in, census + tallies out, copies overlapped with tracking (qsb_stream_*).  Split in two so that a
+// multi-rank driver can run its exchange rounds (qsb_track / qsb_send_slab / qsb_put_arrivals) in between:
+//   qsb_mc_tracking_begin   cycle_begin + stream_begin(processing vault -> device, census -> processed vault)
+//   qsb_mc_tracking_end     stream_end + balance + flux sum into the host model's tallies
+extern "C" int qsb_mc_tracking_begin(qsb_mc* h, qsb_ctx* ctx)
 {
     if (!ctx) return QSB_ERR_ARG;
     return guarded(h, [&](MonteCarlo& mc) {
         auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
         int rc;
         if ((rc = qsb_cycle_begin(ctx, 0)) != QSB_OK) return fail(rc);
-        if ((rc = qsb_put_particles(ctx, mc.processing.data(), mc.processing.size())) != QSB_OK) return fail(rc);
-        if ((rc = qsb_track(ctx, stats)) != QSB_OK) return fail(rc);
+        // the census is delivered straight into the processed vault (page-locked, see MonteCarlo.hh); its size is not
+        // known in advance: start from the input size plus headroom, any excess is fetched at the end
+        const uint64_t n_in = mc.processing.size();
+        uint64_t cap = n_in + n_in / 4 + 65536;
+        if (mc.processed.capacity() > cap) cap = mc.processed.capacity();
+        mc.processed.clear();
+        mc.processed.resize(cap);
+        if ((rc = qsb_stream_begin(ctx, mc.processing.data(), n_in, mc.processed.data(), cap)) != QSB_OK) return fail(rc);
+        return (int)QSB_OK;
+    });
+}
+
+extern "C" int qsb_mc_tracking_end(qsb_mc* h, qsb_ctx* ctx)
+{
+    if (!ctx) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
+        int rc;
         uint64_t n = 0;
-        if ((rc = qsb_census_count(ctx, &n)) != QSB_OK) return fail(rc);
-        h->scratch.resize(n);
-        if ((rc = qsb_get_census(ctx, h->scratch.data(), n, &n)) != QSB_OK) return fail(rc);
+        const uint64_t cap = mc.processed.size();
+        if ((rc = qsb_stream_end(ctx, &n)) != QSB_OK) return fail(rc);
+        if (n > cap)
+        {
+            mc.processed.resize(n);
+            if ((rc = qsb_get_census_range(ctx, cap, mc.processed.data() + cap, n - cap)) != QSB_OK) return fail(rc);
+        }
+        mc.processed.resize(n);
+        mc.processing.clear();
         uint64_t bal[QSB_BAL_COUNT];
         double flux = 0.0;
         if ((rc = qsb_get_balance(ctx, bal)) != QSB_OK) return fail(rc);
         if ((rc = qsb_scalar_flux_sum(ctx, &flux)) != QSB_OK) return fail(rc);
-        return qsb_mc_set_tracking_result(h, h->scratch.data(), n, bal, flux);
+        static const int tracked[] = { QSB_BAL_ABSORB, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_FISSION,
+                                       QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
+        for (int i : tracked) mc.tallies.balanceTask[i] += bal[i];
+        mc.tallies.scalarFluxSum += flux;
+        return (int)QSB_OK;
     });
+}
+
+extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* stats)
+{
+    int rc = qsb_mc_tracking_begin(h, ctx);
+    if (rc != QSB_OK) return rc;
+    if ((rc = qsb_track(ctx, stats)) != QSB_OK)
+    {
+        if (h) h->error = std::string("device: ") + qsb_last_error(ctx);
+        return rc;
+    }
+    return qsb_mc_tracking_end(h, ctx);
 }

@@ -11,10 +11,10 @@ from ._capi import BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE, QsbError
 
 class DeviceContext:
     def __init__(self, image, dt, device=0, validation=True, particle_capacity=0, send_capacity=0,
-                 threads_per_block=0, blocks_per_sm=0, check_geometry=False):
+                 threads_per_block=0, blocks_per_sm=0, check_geometry=False, check_reactions=False):
         self._lib = _capi.lib()
         self.image = image
-        self.opt = _capi.Options(int(bool(validation)), 2 if check_geometry else 0, int(particle_capacity), int(send_capacity),
+        self.opt = _capi.Options(int(bool(validation)), (2 if check_geometry else 0) | (4 if check_reactions else 0), int(particle_capacity), int(send_capacity),
                                  int(threads_per_block), int(blocks_per_sm))
         self._h = C.c_void_p()
         rc = self._lib.qsb_create(int(device), C.byref(image), float(dt), C.byref(self.opt), C.byref(self._h))
@@ -48,6 +48,21 @@ class DeviceContext:
         stats = _capi.TrackStats()
         self._check(self._lib.qsb_track(self._h, C.byref(stats)))
         return stats
+
+    def track_host(self, particles, census_capacity=None):
+        """qsb_track_host: host vault in, census out, copies overlapped with tracking.  Returns (census, stats)."""
+        p = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        cap = int(census_capacity if census_capacity is not None else len(p) + len(p) // 4 + 65536)
+        out = np.empty(cap, dtype=PARTICLE_DTYPE)
+        n = C.c_uint64()
+        stats = _capi.TrackStats()
+        self._check(self._lib.qsb_track_host(self._h, p.ctypes.data_as(C.c_void_p), len(p), out.ctypes.data_as(C.c_void_p), cap,
+                                             C.byref(n), C.byref(stats)))
+        if n.value > cap:
+            more = np.empty(n.value - cap, dtype=PARTICLE_DTYPE)
+            self._check(self._lib.qsb_get_census_range(self._h, cap, more.ctypes.data_as(C.c_void_p), len(more)))
+            out = np.concatenate([out, more])
+        return out[:n.value], stats
 
     def census_count(self):
         n = C.c_uint64()

@@ -95,6 +95,24 @@ class MonteCarlo:
         self._check(self._lib.qsb_mc_cycle_tracking(self._h, ctx._h, C.byref(stats)))
         return stats
 
+    def tracking_begin(self, ctx):
+        """first half of cycle_tracking: processing vault -> device (streamed), census -> processed vault."""
+        self._check(self._lib.qsb_mc_tracking_begin(self._h, ctx._h))
+
+    def tracking_end(self, ctx):
+        """second half: the rest of the census, balance and flux sum into the host model's tallies."""
+        self._check(self._lib.qsb_mc_tracking_end(self._h, ctx._h))
+
+    def processed(self):
+        """the processed vault (this cycle's census) as a structured numpy array (copy)."""
+        n = self.get_int("nProcessed")
+        ptr = C.c_void_p()
+        self._check(self._lib.qsb_mc_processed(self._h, C.byref(ptr), None))
+        if n == 0:
+            return np.zeros(0, dtype=PARTICLE_DTYPE)
+        raw = (C.c_char * (n * PARTICLE_DTYPE.itemsize)).from_address(ptr.value)
+        return np.frombuffer(raw, dtype=PARTICLE_DTYPE).copy()
+
     def cycle_finalize(self):
         row = np.zeros(BAL_COUNT, dtype=np.uint64)
         flux = C.c_double()

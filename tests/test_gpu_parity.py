@@ -25,12 +25,13 @@ CASES = {
 }
 
 
-def _run_case(tmp_path, name, validation=True, check_geometry=False):
+def _run_case(tmp_path, name, validation=True, check_geometry=False, check_reactions=False):
     deck_name, over, cycles = CASES[name]
     deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
     mc = host.MonteCarlo(["-i", deck])
     dt = mc.get_double("dt")
-    ctx = device.DeviceContext(mc.image, dt, validation=validation, particle_capacity=1 << 20, check_geometry=check_geometry)
+    ctx = device.DeviceContext(mc.image, dt, validation=validation, particle_capacity=1 << 20, check_geometry=check_geometry,
+                               check_reactions=check_reactions)
     out = []
     for _ in range(cycles):
         mc.cycle_init()
@@ -76,6 +77,16 @@ def test_filtered_geometry_agrees_with_full_search(tmp_path, name):
         assert np.array_equal(balance, want.balance)
 
 
+@pytest.mark.parametrize("name", ["cts2_small", "p1_small", "p2_small", "nonflat_supercritical", "allabsorb_4dom"])
+def test_direct_reaction_selection_agrees_with_subtraction_chain(tmp_path, name):
+    """check mode: every collision evaluates both the one-division filtered selection and the reference's
+    subtraction chain (src/CollisionEvent.cc:59-83); they must pick the same (isotope, reaction) every time."""
+    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_reactions=True):
+        assert stats.diag["geometry_mismatch"] == 0          # the counter is shared by both check modes
+        assert np.array_equal(balance, want.balance)
+        assert int(balance[BAL["collision"]]) > 0
+
+
 @pytest.mark.parametrize("name", ["cts2_small", "p1_small"])
 def test_fast_build_within_statistical_tolerance(tmp_path, name):
     """fast build (FMA contraction + CUDA libm): histories may differ in the last bits, tallies must agree
@@ -115,4 +126,52 @@ def test_capacity_overflow_is_reported(tmp_path):
     with pytest.raises(host.QsbError) as err:
         ctx.track()
     assert err.value.code == -4
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,census_capacity", [("cts2_small", None), ("nonflat_supercritical", 1000), ("allescape_4dom", None)])
+def test_streamed_host_buffers_match_oracle(tmp_path, name, census_capacity):
+    """qsb_track_host: host vault streamed in (pageable numpy memory -> bounce-buffer staging), census streamed
+    back in record form; with a small census buffer the excess is fetched with qsb_get_census_range."""
+    deck_name, over, _ = CASES[name]
+    deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
+    mc = host.MonteCarlo(["-i", deck])
+    dt = mc.get_double("dt")
+    ctx = device.DeviceContext(mc.image, dt, validation=True, particle_capacity=1 << 20)
+    mc.cycle_init()
+    vault = mc.processing()
+    ctx.cycle_begin()
+    census, stats = ctx.track_host(vault, census_capacity=census_capacity)
+    want = H.oracle_track(mc.image, dt, vault, strict=True, threads=1)
+    assert np.array_equal(ctx.get_balance(), want.balance)
+    assert H.sort_particles(census).tobytes() == H.sort_particles(want.census).tobytes()
+    assert np.allclose(ctx.get_scalar_flux(), want.flux, rtol=FLUX_RTOL, atol=0.0)
+    # the record-form census is also what qsb_get_census returns for this cycle
+    assert H.sort_particles(ctx.get_census()).tobytes() == H.sort_particles(want.census).tobytes()
+    ctx.close()
+
+
+def test_drop_in_streams_whole_census_chunks(tmp_path):
+    """Coral2_P1_1 at its literal size (163 840 particles): the census spans several 65 536-record chunks, so the
+    kernel's chunk-complete flags and the overlapped D2H copies are exercised; two cycles through the drop-in call
+    (page-locked host vaults) against a twin host model driven by the oracle."""
+    deck = decks.write_deck(decks.derive("Coral2_P1_1", nSteps=2), str(tmp_path / "p1.inp"))
+    gpu, cpu = host.MonteCarlo(["-i", deck]), host.MonteCarlo(["-i", deck])
+    dt = gpu.get_double("dt")
+    ctx = device.DeviceContext(gpu.image, dt, validation=True, particle_capacity=1 << 21)
+    import os
+    for cycle in range(2):
+        gpu.cycle_init(), cpu.cycle_init()
+        assert gpu.processing().tobytes() == cpu.processing().tobytes()
+        stats = gpu.cycle_tracking(ctx)
+        want = H.oracle_track(cpu.image, dt, cpu.processing(), strict=True, threads=os.cpu_count() or 1)
+        assert stats.n_census == len(want.census) > 2 * 65536
+        assert H.sort_particles(gpu.processed()).tobytes() == H.sort_particles(want.census).tobytes()
+        cpu.set_tracking_result(want.census, want.balance, want.flux.sum())
+        row_g, flux_g = gpu.cycle_finalize()
+        row_c, flux_c = cpu.cycle_finalize()
+        assert np.array_equal(row_g, row_c)
+        assert abs(flux_g - flux_c) <= 1e-11 * abs(flux_c)
+        # the next cycle must start from identical vaults: carry the oracle's census order into the GPU twin as well
+        gpu.set_tracking_result(want.census, np.zeros(13, np.uint64), 0.0)
     ctx.close()
