@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -182,6 +184,7 @@ struct qsb_ctx
     qsb_base_particle* host_out = nullptr;
     unsigned long long host_out_cap = 0, census_copied = 0;   // records already on their way to host_out
     size_t next_chunk = 0;
+    unsigned chunk_shift = 18;                  // log2(records per streaming chunk), fixed at creation
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
@@ -231,6 +234,13 @@ int guarded(qsb_ctx* c, F&& body)
 
 thread_local std::string g_create_error;
 
+unsigned chunkShiftFromEnv()
+{
+    const char* e = std::getenv("QSB_STREAM_CHUNK_LOG2");
+    const int v = e ? std::atoi(e) : 18;
+    return (unsigned)std::min(std::max(v, 10), 24);
+}
+
 } // namespace
 
 extern "C" {
@@ -261,6 +271,7 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         c->sm_count = prop.multiProcessorCount;
         if (opt) c->opt = *opt; else { c->opt = qsb_options{}; c->opt.validation = 1; }
         c->dt = time_step;
+        c->chunk_shift = chunkShiftFromEnv();
         c->n_ranks = image->n_ranks; c->my_rank = image->my_rank;
         if (c->n_ranks > 64) throw CudaFailure{ "at most 64 ranks supported by the control block" };
         QSB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -301,7 +312,9 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         im.energies = (const double*)place(image->energies, (ng + 1) * 8, b_energy);
         im.xs_total = (const double*)place(image->xs_total, nm * ng * 8, b_total);
         im.xs_react = (const double*)place(image->xs_react, nm * ng * mr * 8, b_react);
-        im.mat_mass = (const double*)place(image->mat_mass, nm * 8, b_mass);
+        std::vector<double> inv_mass(nm);
+        for (size_t m = 0; m < nm; ++m) inv_mass[m] = 1.0 / image->mat_mass[m];
+        im.mat_inv_mass = (const double*)place(inv_mass.data(), nm * 8, b_mass);
         im.mat_nu_bar = (const double*)place(image->mat_nu_bar, nm * 8, b_nubar);
         im.mat_n_iso = (const int*)place(image->mat_n_isotopes, nm * 4, b_niso);
         im.mat_n_react = (const int*)place(image->mat_n_reactions, nm * 4, b_nreact);
@@ -543,8 +556,11 @@ int qsb_put_arrivals(qsb_ctx* c, const void* device_records, uint64_t n)
 
 namespace {
 
-constexpr unsigned kCensusChunkShift = 16;                       // 65 536 records = 8.9 MB per D2H copy
-constexpr size_t kInputChunkRecords = 1u << 16;                  // likewise for the H2D side
+// streaming chunk: 2^18 records = 35.7 MB per DMA copy by default.  Every input chunk is followed by an 8-byte copy that
+// moves ctl->in_ready (stream order), which costs the copy engine a fixed ~20-30 us; at 8.9 MB chunks that was a fifth of the
+// transfer time (measured), at 35.7 MB it is noise, and the pipeline still starts after 0.7 ms.  QSB_STREAM_CHUNK_LOG2 overrides.
+#define kCensusChunkShift (c->chunk_shift)
+#define kInputChunkRecords ((size_t)1 << c->chunk_shift)
 
 bool isPinnedHost(const void* p)
 {
@@ -701,9 +717,16 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         QSB_CUDA(cudaEventRecord(c->ev1, c->stream));
         if (c->streaming)
         {
+            static const bool trace = std::getenv("QSB_TRACE") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             issueStreamInput(c);                                    // H2D of the host vault runs under the kernel
+            const auto t1 = std::chrono::steady_clock::now();
             while (cudaEventQuery(c->ev1) == cudaErrorNotReady) serviceCensus(c, false);   // D2H of finished census chunks too
             QSB_CUDA(cudaGetLastError());
+            if (trace)
+                std::fprintf(stderr, "[qsb] track(streamed): input enqueue %.2f ms, kernel wait %.2f ms, census records already on their way %llu\n",
+                             std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), c->census_copied);
         }
         pullControl(c);
         QSB_CUDA(cudaEventSynchronize(c->ev1));
@@ -741,11 +764,18 @@ int qsb_stream_end(qsb_ctx* c, uint64_t* n_census)
     if (!n_census) return QSB_ERR_ARG;
     return guarded(c, [&]() {
         if (!c->streaming) { c->error = "qsb_stream_end without qsb_stream_begin"; return (int)QSB_ERR_STATE; }
+        static const bool trace = std::getenv("QSB_TRACE") != nullptr;
+        const auto t0 = std::chrono::steady_clock::now();
         pullControl(c);
         *n_census = c->h_ctl->census_count;
+        const unsigned long long before = c->census_copied;
         serviceCensus(c, true);
         QSB_CUDA(cudaStreamSynchronize(c->stream_out));
         QSB_CUDA(cudaStreamSynchronize(c->stream_in));
+        if (trace)
+            std::fprintf(stderr, "[qsb] stream_end: %llu of %llu census records were left to copy, %.2f ms\n",
+                         (unsigned long long)*n_census - before, (unsigned long long)*n_census,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         return (int)QSB_OK;
     });
 }

@@ -50,7 +50,7 @@ struct DevImage
     const double*  energies;        // [n_groups+1]
     const double*  xs_total;        // [n_materials*n_groups]
     const double*  xs_react;        // [n_materials*n_groups*max_react]
-    const double*  mat_mass;        // [n_materials]
+    const double*  mat_inv_mass;    // [n_materials] 1.0 / mass (the reference forms this quotient per scatter, src/NuclearData.cc:66)
     const double*  mat_nu_bar;      // [n_materials]
     const int*     mat_n_iso;       // [n_materials]
     const int*     mat_n_react;     // [n_materials]
@@ -82,15 +82,22 @@ struct ExchangeRecord
 // queue control + tallies, one struct in device memory so a single small copy brings the state back
 struct DevControl
 {
-    unsigned long long head;            // next unclaimed slot of the processing vault
-    unsigned long long tail;            // slots allocated (initial + arrivals + secondaries)
+    // The four queue counters are hit by atomics from every warp on the GPU (together ~20 M per CORAL2 cycle); each sits in
+    // its own 256-byte block so that they are served by different L2 slices instead of queueing on one atomic unit.
+    unsigned long long head;            // next unclaimed ticket of the processing queue
+    unsigned long long pad0[31];
+    unsigned long long tail;            // tickets allocated (streamed records + vault slots: initial, arrivals, secondaries)
+    unsigned long long pad1[31];
     unsigned long long census_count;
+    unsigned long long pad2[31];
     unsigned long long inflight;        // histories created and not yet finished (queued + running); 0 = cycle drained
+    unsigned long long pad3[31];
+    unsigned long long in_ready;        // host-buffer streaming: input records [0, in_ready) have landed in HBM
+    unsigned long long pad4[31];
     unsigned long long slow_geometry;   // segments that took the full 24-facet path
     unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];
     unsigned long long n_lookups;       // diagnostics
-    unsigned long long in_ready;        // host-buffer streaming: input records [0, in_ready) have landed in HBM
     unsigned int overflow;              // bit0 processing vault, bit1 census vault, bit2 send slab
     unsigned int bad_reaction;          // collisions where no reaction was selected (reference: unreachable)
     unsigned int epoch;

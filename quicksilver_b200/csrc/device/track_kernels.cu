@@ -52,6 +52,19 @@ constexpr unsigned long long kNoTicket = ~0ull;
 #define QSB_REFILL 8
 #endif
 constexpr unsigned kRefill = QSB_REFILL;  // idle lanes a warp lets gather before it runs its service phase
+#ifndef QSB_OPT_PREFETCH_L1
+#define QSB_OPT_PREFETCH_L1 1
+#endif
+#ifndef QSB_OPT_PREFETCH_L2
+#define QSB_OPT_PREFETCH_L2 1
+#endif
+#ifndef QSB_OPT_SPARE
+#define QSB_OPT_SPARE 1
+#endif
+#ifndef QSB_COLLIDE
+#define QSB_COLLIDE 20
+#endif
+constexpr unsigned kCollide = QSB_COLLIDE; // lanes with a pending collision a warp lets gather before it runs the collision pass
 constexpr unsigned kTicketBatch = 32;     // tickets a warp reserves per atomicAdd on the queue head
 
 // facet -> 3 of the cell's 14 points, and facet -> matching facet of the face neighbour (src/MC_Domain.cc:41-50)
@@ -79,6 +92,11 @@ __device__ __forceinline__ int cell_iz(const uint4& h) { return (int)(h.y & 0xff
 __device__ __forceinline__ int cell_material(const uint4& h) { return (int)((h.y >> 16) & 0xffu); }
 __device__ __forceinline__ int face_event(const uint4& h, int face) { return (int)((h.z >> (4 * face)) & 0xfu); }
 
+// last_event tag of a raw fission secondary in the vault (see push_raw_child)
+constexpr int kRawChild = 0x52415743;
+// what a lane's in-flight particle needs next
+enum { kStateIdle = 0, kStateSegment = 1, kStateCollision = 2, kStateTail = 3 };
+
 struct Counters     // per-thread balance tallies, flushed once per kernel (src/Tallies.hh:36-100)
 {
     unsigned int segments, collisions, scatters, absorbs, fissions, produced, escapes, census, lookups, slow, mismatch;
@@ -92,9 +110,43 @@ __device__ __forceinline__ double4 load_plane(const double4* __restrict__ p)
     return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// First 16 bytes of a cell record, read on entering the cell.  The record's second sector (facet codes, needed a hundred
+// instructions into the next segment and only then addressable) is pulled into L1 alongside, so that load hits.
 __device__ __forceinline__ uint4 load_cell_head(const DevImage& im, int cell)
 {
-    return __ldg(reinterpret_cast<const uint4*>(im.cells + cell));
+    const char* rec = reinterpret_cast<const char*>(im.cells + cell);
+#if QSB_OPT_PREFETCH_L1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + 32));
+#endif
+    return __ldg(reinterpret_cast<const uint4*>(rec));
+}
+
+// a freshly reserved ticket batch: start moving its particle records towards L2 (lane i takes ticket first + i)
+__device__ __forceinline__ void prefetch_tickets(const TrackArgs& a, unsigned long long first, unsigned lane)
+{
+    const unsigned long long t = first + lane;
+    if (t < a.n_in)
+    {
+        const char* rec = reinterpret_cast<const char*>(a.in_aos + t);
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(rec));
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(rec + 128));
+    }
+    else if (t - a.n_in < a.proc.capacity)
+    {
+        const unsigned long long i = t - a.n_in;
+        const VaultView& v = a.proc;
+        // one lane in four touches each 32-byte sector of the 8-byte arrays
+        if ((lane & 3u) == 0u)
+        {
+            const double* f64[15] = { v.x, v.y, v.z, v.vx, v.vy, v.vz, v.energy, v.weight, v.ttc, v.age, v.nmfp, v.nseg, v.dirx, v.diry, v.dirz };
+#pragma unroll
+            for (int k = 0; k < 15; ++k) asm volatile("prefetch.global.L2 [%0];" :: "l"(f64[k] + i));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(v.seed + i));
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(v.id + i));
+        }
+        if ((lane & 1u) == 0u) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.tags + i));
+        if ((lane & 7u) == 0u) asm volatile("prefetch.global.L2 [%0];" :: "l"(v.cell + i));
+    }
 }
 
 // log / sin / cos: the portable functions of qs_strict_math.h in BOTH builds.  Validation (--fmad=false) gets the bits
@@ -102,6 +154,37 @@ __device__ __forceinline__ uint4 load_cell_head(const DevImage& im, int cell)
 // out-of-line argument-reduction slow path, which the tracking loop can never reach (0 <= phi < 2 pi, 0 < r < 1).
 __device__ __forceinline__ double m_log(double x) { return qs_strict_log(x); }
 __device__ __forceinline__ void m_sincos(double phi, double* s, double* c) { qs_strict_sincos(phi, s, c); }
+
+// Arithmetic that differs between the two builds.  Validation: IEEE division and square root exactly as the reference
+// (and the oracle) evaluate them.  Fast: the hardware reciprocal / reciprocal-square-root approximation refined by two
+// Newton / Goldschmidt steps in FMA arithmetic (relative error ~1e-15, branch-free, a third of the instructions).
+__device__ __forceinline__ double approx_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = __fma_rn(-x, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-x, r, 1.0);
+    return __fma_rn(r, e, r);
+}
+__device__ __forceinline__ double approx_sqrt(double x)
+{
+    x = fmax(x, 1e-300);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = __fma_rn(-g, h, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    r = __fma_rn(-g, h, 0.5);
+    return __fma_rn(g, r, g);
+}
+#if QSB_VALIDATION
+__device__ __forceinline__ double m_div(double a, double b) { return a / b; }
+__device__ __forceinline__ double m_sqrt(double x) { return sqrt(x); }
+#else
+__device__ __forceinline__ double m_div(double a, double b) { return a * approx_rcp(b); }
+__device__ __forceinline__ double m_sqrt(double x) { return approx_sqrt(x); }
+#endif
 
 // src/NuclearData.cc:208-227.  The reference bisects the nGroups+1 edges: for e[0] < energy <= e[n-1] it returns the
 // largest i <= n-2 with e[i] <= energy.  The edges are log-spaced (src/NuclearData.cc:105-119), so the index is first
@@ -121,7 +204,7 @@ __device__ __forceinline__ int energy_group(const DevImage& im, double energy)
     return i;
 }
 
-__device__ __forceinline__ double speed_of(const Particle& p) { return sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz); }
+__device__ __forceinline__ double speed_of(const Particle& p) { return m_sqrt(p.vx * p.vx + p.vy * p.vy + p.vz * p.vz); }
 
 // MC_Load_Particle + MC_Particle(const MC_Base_Particle&): src/MC_Load_Particle.cc:11-29,
 // src/MC_Base_Particle.hh:287-331
@@ -130,7 +213,7 @@ __device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p
     p.speed = speed_of(p);
     if (derive_direction)
     {
-        const double factor = 1.0 / p.speed;
+        const double factor = m_div(1.0, p.speed);
         p.alpha = factor * p.vx; p.beta = factor * p.vy; p.gamma = factor * p.vz;
     }
     if (p.ttc <= 0.0) p.ttc += dt;
@@ -138,7 +221,7 @@ __device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p
     p.group = energy_group(im, p.energy);
 }
 
-__device__ __forceinline__ void load_particle(const TrackArgs& a, unsigned long long i, Particle& p)
+__device__ __forceinline__ int load_particle(const TrackArgs& a, unsigned long long i, Particle& p)
 {
     const VaultView& v = a.proc;
     p.x = __ldcg(v.x + i); p.y = __ldcg(v.y + i); p.z = __ldcg(v.z + i);
@@ -152,7 +235,9 @@ __device__ __forceinline__ void load_particle(const TrackArgs& a, unsigned long 
     p.alpha = __ldcg(v.dirx + i); p.beta = __ldcg(v.diry + i); p.gamma = __ldcg(v.dirz + i);
     p.facet = 0; p.total_xs = 0.0;
     p.head = load_cell_head(a.im, p.cell);
+    if (p.last_event == kRawChild) { p.last_event = QSB_EV_COLLISION; p.speed = 0.0; p.group = 0; return kStateTail; }
     reload_transform(a.im, p, a.dt, p.alpha != p.alpha);
+    return kStateSegment;
 }
 
 // host-buffer streaming: ticket i is record i of the host vault, DMA-copied into HBM as it is (136-byte
@@ -329,7 +414,7 @@ __device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Par
     if (az > 0 && (w < 0 || gz * aw < gw * az)) { w = 2; gw = gz; aw = az; }
     if (w < 0) return false;
     ok = ok && gw > m;
-    const double t = gw / aw;                      // approximate distance: only used for the filter
+    const double t = gw * approx_rcp(aw);          // approximate distance (~1e-15 relative): only used for the filter
     const double ex = p.x + t * p.alpha, ey = p.y + t * p.beta, ez = p.z + t * p.gamma;
 
     // normalised in-face coordinates of the exit point, (u, v) = the two other axes in x<y<z order
@@ -358,7 +443,7 @@ __device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Par
     const double D = (face & 1) ? d_abs : -d_abs;
     const double numerator = -1.0 * (normal * pw + D);
     const double dot = normal * dw;
-    const double dist = numerator / dot;
+    const double dist = m_div(numerator, dot);
     if (!(fabs(dist - t) <= 1e-9 * (t + m))) return false;   // also catches NaN
     facet = f; distance = dist;
     return true;
@@ -409,7 +494,11 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
     if (d_census < dmin) { dmin = d_census; outcome = 2; }
 
     const double segment_path_length = dmin;
+#if QSB_VALIDATION
     p.nmfp -= segment_path_length / mean_free_path;
+#else
+    p.nmfp -= segment_path_length * ((xs.x == 0.0) ? 1.0 / kHugeDouble : xs.x);
+#endif
     p.last_event = outcome == 0 ? QSB_EV_COLLISION : (outcome == 1 ? QSB_EV_FACET_TRANSIT : QSB_EV_CENSUS);
     if (outcome == 0) p.nmfp = 0.0;
     else if (outcome == 1) p.facet = nf_facet;
@@ -421,7 +510,7 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
     p.x += (p.alpha * segment_path_length);
     p.y += (p.beta * segment_path_length);
     p.z += (p.gamma * segment_path_length);
-    const double segment_path_time = (segment_path_length / particle_speed);
+    const double segment_path_time = m_div(segment_path_length, particle_speed);
     p.ttc -= segment_path_time;
     p.age += segment_path_time;
     if (p.ttc < 0.0) p.ttc = 0.0;
@@ -432,7 +521,9 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
 }
 
 // ---- collision ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void update_trajectory(double energy, double angle, Particle& p)
+// updateTrajectory (src/CollisionEvent.cc:25-45) + DirectionCosine::Rotate3DVector (src/DirectionCosine.hh:123-146).
+// Returns the speed the new velocity was built from.
+__device__ __forceinline__ double update_trajectory(double energy, double angle, Particle& p)
 {
     p.energy = energy;
     const double cosTheta = angle;
@@ -440,36 +531,73 @@ __device__ __forceinline__ void update_trajectory(double energy, double angle, P
     const double phi = 2 * 3.14159265 * r;
     double sinPhi, cosPhi;
     m_sincos(phi, &sinPhi, &cosPhi);
-    const double sinTheta = sqrt((1.0 - (cosTheta * cosTheta)));
+    const double sinTheta = m_sqrt((1.0 - (cosTheta * cosTheta)));
 
     const double cos_theta = p.gamma;
-    const double sin_theta = sqrt((1.0 - (cos_theta * cos_theta)));
+    const double sin_theta = m_sqrt((1.0 - (cos_theta * cos_theta)));
     double cos_phi, sin_phi;
     if (sin_theta < 1e-6) { cos_phi = 1.0; sin_phi = 0.0; }
-    else { cos_phi = p.alpha / sin_theta; sin_phi = p.beta / sin_theta; }
+    else
+    {
+#if QSB_VALIDATION
+        cos_phi = p.alpha / sin_theta; sin_phi = p.beta / sin_theta;
+#else
+        const double inv = approx_rcp(sin_theta);
+        cos_phi = p.alpha * inv; sin_phi = p.beta * inv;
+#endif
+    }
     const double na =  cos_theta * cos_phi * (sinTheta * cosPhi) - sin_phi * (sinTheta * sinPhi) + sin_theta * cos_phi * cosTheta;
     const double nb =  cos_theta * sin_phi * (sinTheta * cosPhi) + cos_phi * (sinTheta * sinPhi) + sin_theta * sin_phi * cosTheta;
     const double ng = -sin_theta           * (sinTheta * cosPhi) +                                 cos_theta           * cosTheta;
     p.alpha = na; p.beta = nb; p.gamma = ng;
 
+#if QSB_VALIDATION
     const double speed = (kSpeedOfLight *
                           sqrt((1.0 - ((kNeutronRestMassEnergy * kNeutronRestMassEnergy) /
                                        ((energy + kNeutronRestMassEnergy) * (energy + kNeutronRestMassEnergy))))));
+#else
+    const double ratio = kNeutronRestMassEnergy * approx_rcp(energy + kNeutronRestMassEnergy);
+    const double speed = kSpeedOfLight * approx_sqrt(1.0 - ratio * ratio);
+#endif
     p.vx = speed * p.alpha; p.vy = speed * p.beta; p.vz = speed * p.gamma;
     r = qs_rng_sample(&p.seed);
     p.nmfp = -1.0 * m_log(r);
+    return speed;
 }
 
-// append a secondary to the processing vault: count it in flight, write it, then publish the slot
-__device__ __forceinline__ void push_secondary(const TrackArgs& a, const Particle& child, uint32_t epoch)
+// A fission secondary is appended to the processing vault "raw": the parent's state at the collision, the child's own
+// random-number stream, and the outgoing energy / scattering cosine sampled for it (in the energy and nmfp fields), tagged
+// kRawChild.  The reference computes the child's updateTrajectory right here in the parent's thread
+// (src/CollisionEvent.cc:125-133); that is two draws from the CHILD's stream and touches nothing of the parent, so it is
+// done instead by whichever lane loads the record, inside the converged collision-tail pass -- same arithmetic, same
+// bits, but not a 300-instruction detour with one lane active.  Slots are handed out per warp (one atomic for all the
+// secondaries of a collision pass), records are written at once and published one pass later (publish_children).
+
+__device__ __forceinline__ void write_raw_child(const TrackArgs& a, unsigned long long i, const Particle& parent, uint64_t child_seed,
+                                                double energy_out, double angle_out)
 {
-    const unsigned long long slot = atomicAdd(&a.ctl->tail, 1ull) - a.n_in;     // tickets below n_in are the streamed host records
-    if (slot >= a.proc.capacity) { atomicOr(&a.ctl->overflow, 1u); return; }
-    atomicAdd(&a.ctl->inflight, 1ull);
-    store_particle(a.proc, slot, child, false);
-    // publish: release store (MEMBAR.ALL.GPU + STG, no L1 invalidation -- __threadfence() would add CCTL.IVALL and
-    // throw away this SM's cached cell records and cross-section tables on every fission)
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.proc.ready + slot), "r"(epoch) : "memory");
+    const VaultView& v = a.proc;
+    __stcg(v.x + i, parent.x); __stcg(v.y + i, parent.y); __stcg(v.z + i, parent.z);
+    __stcg(v.vx + i, parent.vx); __stcg(v.vy + i, parent.vy); __stcg(v.vz + i, parent.vz);
+    __stcg(v.energy + i, energy_out); __stcg(v.weight + i, parent.weight); __stcg(v.ttc + i, parent.ttc);
+    __stcg(v.age + i, parent.age); __stcg(v.nmfp + i, angle_out); __stcg(v.nseg + i, parent.nseg);
+    __stcg(v.seed + i, (unsigned long long)child_seed); __stcg(v.id + i, (unsigned long long)child_seed);
+    __stcg(v.cell + i, parent.cell);
+    __stcg(v.tags + i, make_int4(kRawChild, parent.num_collisions, parent.breed, parent.species));
+    __stcg(v.dirx + i, parent.alpha); __stcg(v.diry + i, parent.beta); __stcg(v.dirz + i, parent.gamma);
+}
+
+// Publish the secondaries this lane wrote in an earlier pass (slots [first, first + n)): one release store -- MEMBAR.ALL.GPU
+// + STG, no L1 invalidation (__threadfence() would add CCTL.IVALL and throw away the SM's cached cell records and tables) --
+// then relaxed stores for the rest.  Done one pass late and for the whole warp at once: by then the record stores have long
+// been acknowledged, so the barrier no longer waits a DRAM round trip per fission (measured: 2.4 us each, 12 % of all stall
+// samples, when every fissioning lane published on the spot).
+__device__ __forceinline__ void publish_children(const TrackArgs& a, unsigned long long first, unsigned n, uint32_t epoch)
+{
+    if (n == 0u) return;
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(a.proc.ready + first), "r"(epoch) : "memory");
+    for (unsigned k = 1; k < n; ++k)
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(a.proc.ready + first + k), "r"(epoch) : "memory");
 }
 
 // The reference walks the material's (isotope, reaction) table subtracting each macroscopic cross section until
@@ -557,8 +685,11 @@ __device__ __forceinline__ int select_reaction_generic(const double* __restrict_
     return -1;
 }
 
-// returns true when the particle keeps tracking
-__device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p, Counters& c, uint32_t epoch)
+// Collision, first half (src/CollisionEvent.cc:50-133): pick the reaction, sample its outcome, tally, spawn the
+// outgoing particles.  Returns their number (0: the history ends here) and their (energy, scattering cosine) pairs: pair 0
+// is the parent's own, for collision_tail; pairs 1.. belong to the secondaries the caller spawns.
+__device__ __forceinline__ int collision_head(const TrackArgs& a, Particle& p, Counters& c, double& energy0, double& angle0,
+                                               double& energy1, double& angle1, double& energy2, double& angle2, double& energy3, double& angle3)
 {
     const DevImage& im = a.im;
     const int mat = cell_material(p.head);
@@ -574,16 +705,17 @@ __device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p,
     else if (periodic && n_react <= 9) selected = select_reaction_periodic<9>(table, n_iso, n_react, current, p.total_xs, check, c.mismatch);
     else                               selected = select_reaction_generic(table, n_iso * n_react, current);
     c.lookups += (selected < 0 ? n_iso * n_react : selected + 1);
-    if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return false; }
+    if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return 0; }
 
-    double energyOut[4], angleOut[4];
+    // NuclearDataReaction::sampleCollision (src/NuclearData.cc:54-88)
+    double energyOut[4] = { 0.0, 0.0, 0.0, 0.0 }, angleOut[4] = { 0.0, 0.0, 0.0, 0.0 };
     int nOut = 0;
     const int rtype = __ldg(im.mat_react_type + (size_t)mat * im.max_react + selected);
     if (rtype == QSB_REACT_SCATTER)
     {
         nOut = 1;
         r = qs_rng_sample(&p.seed);
-        energyOut[0] = p.energy * (1.0 - (r * (1.0 / __ldg(im.mat_mass + mat))));
+        energyOut[0] = p.energy * (1.0 - (r * __ldg(im.mat_inv_mass + mat)));     // r * (1.0 / mass), the quotient formed on the host
         r = qs_rng_sample(&p.seed) * 2.0 - 1.0;
         angleOut[0] = r;
     }
@@ -610,29 +742,37 @@ __device__ __forceinline__ bool collision_event(const TrackArgs& a, Particle& p,
     else if (rtype == QSB_REACT_ABSORPTION) c.absorbs++;
     else if (rtype == QSB_REACT_FISSION) { c.fissions++; c.produced += nOut; }
 
-    if (nOut == 0) return false;
+    energy0 = energyOut[0]; angle0 = angleOut[0];
+    energy1 = energyOut[1]; angle1 = angleOut[1];
+    energy2 = energyOut[2]; angle2 = angleOut[2];
+    energy3 = energyOut[3]; angle3 = angleOut[3];
+    return nOut;
+}
 
-#pragma unroll 1
-    for (int s = 1; s < nOut; ++s)
-    {
-        Particle child = p;
-        child.seed = qs_rng_spawn(&p.seed);
-        child.id = child.seed;
-        update_trajectory(s == 1 ? energyOut[1] : (s == 2 ? energyOut[2] : energyOut[3]),
-                          s == 1 ? angleOut[1] : (s == 2 ? angleOut[2] : angleOut[3]), child);
-        push_secondary(a, child, epoch);
-    }
-    update_trajectory(energyOut[0], angleOut[0], p);
-    if (nOut > 1)
-    {
-        // the reference re-queues the fissioning parent as a base particle and loads it again later:
-        // direction cosine re-derived from the velocity, census clock / age fixed up
-        reload_transform(im, p, a.dt, true);
-        return true;
-    }
+// Collision, second half: the outgoing particle's new trajectory (src/CollisionEvent.cc:135-145).  `requeued` marks a
+// particle that the reference stores as a base particle and loads again before it flies on -- the fissioning parent
+// (src/CollisionEvent.cc:137-142) and every secondary (raw child records) -- i.e. MC_Load_Particle's transform on top:
+// direction cosine re-derived from the velocity, census clock / age fixed up (parity hazards 1-2 of SURVEY.md 8a).
+__device__ __forceinline__ void collision_tail(const TrackArgs& a, Particle& p, double energy0, double angle0, bool requeued)
+{
+    const double speed = update_trajectory(energy0, angle0, p);
+#if QSB_VALIDATION
+    (void)speed;
     p.speed = speed_of(p);
-    p.group = energy_group(im, p.energy);
-    return true;
+    if (requeued)
+    {
+        const double factor = 1.0 / p.speed;
+        p.alpha = factor * p.vx; p.beta = factor * p.vy; p.gamma = factor * p.vz;
+    }
+#else
+    p.speed = speed;            // |velocity| up to rounding; the direction cosine is already a unit vector
+#endif
+    if (requeued)
+    {
+        if (p.ttc <= 0.0) p.ttc += a.dt;
+        if (p.age < 0.0) p.age = 0.0;
+    }
+    p.group = energy_group(a.im, p.energy);
 }
 
 // ---- facet crossing --------------------------------------------------------------------------------------
@@ -731,34 +871,32 @@ __device__ __forceinline__ void store_census_aos(const DevImage& im, qsb_base_pa
     __stcg(u + 16, (unsigned long long)(unsigned)d | ((unsigned long long)(unsigned)local << 32));
 }
 
-// Census append, executed in the warp's service phase by all lanes whose history ended at census since the last
-// service phase (`pending`), converged: one atomic for the group, one record per lane -- SoA vault, or the record-form
+// Census append.  Slots are allocated in the segment pass that ends the histories (one atomic per warp and pass, issued
+// by the lowest such lane and NOT waited for: its return value is first read here, a pass or more later); the records are
+// stored in the warp's next service phase by all lanes with a pending census, converged -- SoA vault, or the record-form
 // buffer when the census is being streamed to the host.
-__device__ __forceinline__ void census_flush(const TrackArgs& a, const Particle& p, bool pending, unsigned lane)
+__device__ __forceinline__ void census_flush(const TrackArgs& a, const Particle& p, bool pending, unsigned lane,
+                                             unsigned long long my_base, unsigned my_count, unsigned leader, unsigned rank)
 {
     const unsigned group = __ballot_sync(kFullMask, pending);
     if (group == 0u) return;
-    const int leader = __ffs(group) - 1;
-    const unsigned n = __popc(group);
-    unsigned long long base = 0;
-    if ((int)lane == leader) base = atomicAdd(&a.ctl->census_count, (unsigned long long)n);
-    base = __shfl_sync(kFullMask, base, leader);
+    const unsigned long long base = __shfl_sync(kFullMask, my_base, leader);   // each lane reads the base its own group's leader holds
     if (pending)
     {
-        const unsigned long long slot = base + __popc(group & ((1u << lane) - 1u));
+        const unsigned long long slot = base + rank;
         if (slot >= a.census.capacity) atomicOr(&a.ctl->overflow, 2u);
         else if (a.census_aos) store_census_aos(a.im, a.census_aos + slot, p);
         else store_particle(a.census, slot, p, false);
     }
     if (!a.census_aos) return;
-    // streaming: count the group's records into their chunk(s) with release semantics -- the records of the whole
-    // group (same warp, ordered by the __syncwarp) are visible before the count -- and tell the host about every chunk
+    // streaming: count each group's records into their chunk(s) with release semantics -- the records of the whole
+    // warp (ordered by the __syncwarp) are visible before the count -- and tell the host about every chunk
     // that became complete, through mapped pinned memory; its D2H copy then runs while tracking continues
     __syncwarp();
-    if ((int)lane == leader)
+    if (pending && my_count != 0u)                    // group leaders
     {
-        const unsigned long long last = min(base + n, a.census.capacity);
-        unsigned long long at = base;
+        const unsigned long long last = min(my_base + my_count, a.census.capacity);
+        unsigned long long at = my_base;
         while (at < last)
         {
             const unsigned long long chunk = at >> a.census_chunk_shift;
@@ -785,7 +923,6 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
     const unsigned lane = threadIdx.x & 31u;
     Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     Particle p;
-    bool have = false;
     unsigned long long ticket = kNoTicket;
     unsigned long long pool_next = 0, pool_end = 0;     // warp-uniform: tickets reserved by this warp, not yet handed to a lane
     unsigned long long in_seen = 0;                     // last value of ctl->in_ready this lane has seen
@@ -793,23 +930,39 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
     unsigned backoff = 64;
 
     bool census_pending = false;                        // history ended at census; the record is still in this lane's registers
+    unsigned long long census_base = 0;                 // leader of a census group: first slot of the group (return value of its atomic)
+    unsigned census_count = 0, census_leader = 0, census_rank = 0;
+    unsigned long long pub_first = 0;                   // secondaries written in the last collision pass, not yet published
+    unsigned pub_n = 0;
+    unsigned long long spare_base = 0;                  // lane 0: the next ticket batch, reserved one service phase ahead
+    bool spare_valid = false;
+    int state = kStateIdle;                             // what this lane's particle needs next (kState*)
+    unsigned retired = 0;                               // warp-uniform: histories finished since the last service phase
 
     for (;;)
     {
         __syncwarp();
+        if (__ballot_sync(kFullMask, pub_n != 0u)) { publish_children(a, pub_first, pub_n, epoch); pub_n = 0u; }
+
         // SERVICE PHASE.  Ending a history (census store) and starting one (ticket, particle load, reload transform, energy
         // group) are long code paths that single lanes reach at random times; run per lane as they come they would each cost
         // the warp a full pass with one or two lanes active (measured: a third of all issue slots).  Idle lanes therefore wait
         // until kRefill of them have gathered (or nothing is left to track) and then do it together, converged.
-        const unsigned idle_mask = __ballot_sync(kFullMask, !have);
+        const unsigned idle_mask = __ballot_sync(kFullMask, state == kStateIdle);
         if (__popc(idle_mask) >= kRefill || idle_mask == kFullMask)
         {
-            census_flush(a, p, census_pending, lane);
-            census_pending = false;
+            // retire the histories that finished since the last service phase: one reduction per warp.  Secondaries were
+            // counted before they became visible, so inflight reaches 0 only when nothing is queued or running.
+            if (retired && lane == 0) atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)retired);
+            retired = 0u;
+            census_flush(a, p, census_pending, lane, census_base, census_count, census_leader, census_rank);
+            census_pending = false; census_count = 0u;
 
-            // 1. every idle lane without a ticket takes one from the warp's pool; the pool is refilled kTicketBatch tickets at a
-            //    time with a single atomicAdd (a reserved ticket is an obligation: it is always handed to a lane eventually)
-            const bool want = !have && ticket == kNoTicket;
+            // 1. every idle lane without a ticket takes one from the warp's pool.  The pool is refilled kTicketBatch tickets at a
+            //    time from a batch that was reserved during the PREVIOUS service phase (one atomicAdd whose return value is
+            //    only read now, so its latency is off the critical path).  A reserved ticket is an obligation: it is always
+            //    handed to a lane eventually.
+            const bool want = state == kStateIdle && ticket == kNoTicket;
             const unsigned want_mask = __ballot_sync(kFullMask, want);
             if (want_mask)
             {
@@ -818,13 +971,19 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                 unsigned long long fresh = 0;
                 if (n_want > avail)
                 {
-                    if (lane == 0) fresh = atomicAdd(&a.ctl->head, (unsigned long long)kTicketBatch);
-                    fresh = __shfl_sync(kFullMask, fresh, 0);
+                    if (!spare_valid && lane == 0) spare_base = atomicAdd(&a.ctl->head, (unsigned long long)kTicketBatch);
+                    fresh = __shfl_sync(kFullMask, spare_base, 0);
+                    spare_valid = false;
                 }
                 const unsigned rank = __popc(want_mask & ((1u << lane) - 1u));
                 if (want) ticket = rank < avail ? pool_next + rank : fresh + (rank - avail);
-                if (n_want > avail) { pool_next = fresh + (n_want - avail); pool_end = fresh + kTicketBatch; }
+                if (n_want > avail) { pool_next = fresh + (n_want - avail); pool_end = fresh + kTicketBatch; if (QSB_OPT_PREFETCH_L2) prefetch_tickets(a, fresh, lane); }
                 else pool_next += n_want;
+            }
+            if (QSB_OPT_SPARE && !spare_valid)
+            {
+                if (lane == 0) spare_base = atomicAdd(&a.ctl->head, (unsigned long long)kTicketBatch);
+                spare_valid = true;
             }
             // 2. redeem.  A streamed host record is there once the DMA front (ctl->in_ready) has passed it; a vault slot is ready
             //    if the host wrote it (below ready_prefix) or its ready word carries this epoch.  The flag is read with a relaxed
@@ -832,7 +991,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             //    before the flag value has come back, and the writer released the flag after the data, so no fence (and no L1
             //    invalidation) is needed on this side.
             bool ready = false;
-            if (!have && ticket != kNoTicket)
+            if (state == kStateIdle && ticket != kNoTicket)
             {
                 if (ticket < a.n_in)
                 {
@@ -854,12 +1013,11 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             }
             if (ready)
             {
-                if (ticket < a.n_in) load_particle_aos(a, ticket, p);
-                else load_particle(a, ticket - a.n_in, p);
-                have = true;
+                if (ticket < a.n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
+                else state = load_particle(a, ticket - a.n_in, p);
                 ticket = kNoTicket;
             }
-            if (__ballot_sync(kFullMask, have) == 0u)
+            if (__ballot_sync(kFullMask, state != kStateIdle) == 0u)
             {
                 // idle warp: the cycle is over when no history is queued or running anywhere on this GPU
                 unsigned long long inflight = 1;
@@ -873,23 +1031,96 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             backoff = 64;
         }
 
+        // TRACKING PHASE, one of two passes per iteration.  A segment ends in a collision about every other time, and the
+        // collision code is the longest path of the loop; run straight after each segment it would see half the lanes.  Lanes
+        // whose segment ended in a collision therefore wait (kStateCollision), together with freshly loaded secondaries that
+        // still need their outgoing trajectory (kStateTail), until kCollide of them have gathered or no lane is left that can
+        // advance by a segment; then the warp runs one collision pass for all of them.
         bool finished = false;
-        if (have)
+        const unsigned seg_mask = __ballot_sync(kFullMask, state == kStateSegment);
+        const unsigned col_mask = __ballot_sync(kFullMask, state >= kStateCollision);
+        if (__popc(col_mask) >= kCollide || seg_mask == 0u)
         {
-            const int outcome = segment_outcome(a, p, c);
-            c.segments++;
-            p.nseg += 1.;
-            bool keep;
-            if (outcome == 0) keep = collision_event(a, p, c, epoch);
-            else if (outcome == 1) keep = facet_crossing_event(a, p, c);
-            else { census_pending = true; c.census++; keep = false; }     // stored in the next service phase
-            have = keep;
-            finished = !keep;
+            double energy0 = p.energy, angle0 = p.nmfp;             // a raw child carries its sampled outcome in these two fields
+            double energy1 = 0.0, angle1 = 0.0, energy2 = 0.0, angle2 = 0.0, energy3 = 0.0, angle3 = 0.0;
+            int n_out = 1;
+            if (state == kStateCollision)
+                n_out = collision_head(a, p, c, energy0, angle0, energy1, angle1, energy2, angle2, energy3, angle3);
+            // secondaries of the whole pass: vault slots and the in-flight count with one atomic each per warp
+            const unsigned n_child = (state == kStateCollision && n_out > 1) ? (unsigned)(n_out - 1) : 0u;
+            unsigned incl = n_child;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const unsigned up = __shfl_up_sync(kFullMask, incl, d);
+                if ((int)lane >= d) incl += up;
+            }
+            const unsigned total = __shfl_sync(kFullMask, incl, 31);
+            if (total)
+            {
+                unsigned long long base = 0;
+                if (lane == 0)
+                {
+                    base = atomicAdd(&a.ctl->tail, (unsigned long long)total);
+                    atomicAdd(&a.ctl->inflight, (unsigned long long)total);
+                }
+                base = __shfl_sync(kFullMask, base, 0) - a.n_in;     // tickets below n_in are the streamed host records
+                if (n_child)
+                {
+                    const unsigned long long first = base + (incl - n_child);
+                    if (first + n_child > a.proc.capacity)
+                    {
+                        atomicOr(&a.ctl->overflow, 1u);
+                        atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)n_child);
+                    }
+                    else
+                    {
+                        // seeds spawned from the parent's stream in order, before the parent's own trajectory draws
+                        // (src/CollisionEvent.cc:125-135)
+                        write_raw_child(a, first, p, qs_rng_spawn(&p.seed), energy1, angle1);
+                        if (n_child > 1u) write_raw_child(a, first + 1, p, qs_rng_spawn(&p.seed), energy2, angle2);
+                        if (n_child > 2u) write_raw_child(a, first + 2, p, qs_rng_spawn(&p.seed), energy3, angle3);
+                        pub_first = first; pub_n = n_child;
+                    }
+                }
+            }
+            if (state >= kStateCollision)
+            {
+                if (n_out > 0) { collision_tail(a, p, energy0, angle0, state == kStateTail || n_out > 1); state = kStateSegment; }
+                else { state = kStateIdle; finished = true; }
+            }
         }
-        // 3. retire finished histories: one reduction per warp.  Secondaries were counted before they became
-        //    visible (push_secondary), so inflight reaches 0 only when nothing is queued or running.
-        const unsigned fin_mask = __ballot_sync(kFullMask, finished);
-        if (fin_mask && lane == 0) atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)__popc(fin_mask));
+        else
+        {
+            int outcome = -1;
+            if (state == kStateSegment)
+            {
+                outcome = segment_outcome(a, p, c);
+                c.segments++;
+                p.nseg += 1.;
+                if (outcome == 0) state = kStateCollision;
+                else if (outcome == 1) { if (!facet_crossing_event(a, p, c)) { state = kStateIdle; finished = true; } }
+                else { census_pending = true; c.census++; state = kStateIdle; finished = true; }     // stored in the next service phase
+            }
+            // census slots for the histories that just ended: one atomic per warp, its result is not read before the service phase
+            const unsigned cen_mask = __ballot_sync(kFullMask, outcome == 2);
+            if (cen_mask)
+            {
+                const unsigned leader = __ffs(cen_mask) - 1;
+                if (outcome == 2)
+                {
+                    census_leader = leader;
+                    census_rank = __popc(cen_mask & ((1u << lane) - 1u));
+                    if (lane == leader)
+                    {
+                        census_count = __popc(cen_mask);
+                        census_base = atomicAdd(&a.ctl->census_count, (unsigned long long)census_count);
+                    }
+                }
+            }
+        }
+        // finished histories are retired (subtracted from the global in-flight count) in the next service phase
+        retired += __popc(__ballot_sync(kFullMask, finished));
     }
 
     // flush the per-thread balance counters: warp sum, one atomic per counter per warp

@@ -1,6 +1,8 @@
 // capi_host.cc -- extern "C" entry points of the host model (qsb_mc_*), see include/qsb.h.
 // Every entry point catches exceptions and reports through the return code + qsb_mc_last_error.
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <new>
@@ -270,12 +272,22 @@ extern "C" int qsb_mc_tracking_end(qsb_mc* h, qsb_ctx* ctx)
 
 extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* stats)
 {
+    static const bool trace = std::getenv("QSB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     int rc = qsb_mc_tracking_begin(h, ctx);
     if (rc != QSB_OK) return rc;
-    if ((rc = qsb_track(ctx, stats)) != QSB_OK)
+    const double t1 = now();
+    qsb_track_stats local;
+    if ((rc = qsb_track(ctx, stats ? stats : &local)) != QSB_OK)
     {
         if (h) h->error = std::string("device: ") + qsb_last_error(ctx);
         return rc;
     }
-    return qsb_mc_tracking_end(h, ctx);
+    const double t2 = now();
+    rc = qsb_mc_tracking_end(h, ctx);
+    if (trace)
+        std::fprintf(stderr, "[qsb] cycle_tracking: begin %.2f ms, track %.2f ms (kernel %.2f ms), end %.2f ms\n", t1 - t0, t2 - t1,
+                     (double)(stats ? stats->device_ms : local.device_ms), now() - t2);
+    return rc;
 }

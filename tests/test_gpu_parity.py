@@ -151,13 +151,14 @@ def test_streamed_host_buffers_match_oracle(tmp_path, name, census_capacity):
     ctx.close()
 
 
-def test_drop_in_streams_whole_census_chunks(tmp_path):
-    """Coral2_P1_1 at its literal size (163 840 particles): the census spans several 65 536-record chunks, so the
+def test_drop_in_streams_whole_census_chunks(tmp_path, monkeypatch):
+    """Coral2_P1_1 at its literal size (163 840 particles) with 16 384-record streaming chunks: the vault and the census span many chunks, so the
     kernel's chunk-complete flags and the overlapped D2H copies are exercised; two cycles through the drop-in call
     (page-locked host vaults) against a twin host model driven by the oracle."""
     deck = decks.write_deck(decks.derive("Coral2_P1_1", nSteps=2), str(tmp_path / "p1.inp"))
     gpu, cpu = host.MonteCarlo(["-i", deck]), host.MonteCarlo(["-i", deck])
     dt = gpu.get_double("dt")
+    monkeypatch.setenv("QSB_STREAM_CHUNK_LOG2", "14")        # read when the context is created
     ctx = device.DeviceContext(gpu.image, dt, validation=True, particle_capacity=1 << 21)
     import os
     for cycle in range(2):
