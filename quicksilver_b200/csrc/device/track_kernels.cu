@@ -86,6 +86,18 @@ struct Particle
     int last_event, num_collisions, breed, species;
 };
 
+// Velocity of an in-flight particle.  Validation: the stored vector, exactly as the reference carries it.  Fast build:
+// speed * direction cosine (equal up to rounding), so the three velocity registers are not live across the tracking loop.
+#if QSB_VALIDATION
+#define QSB_VX(p_) ((p_).vx)
+#define QSB_VY(p_) ((p_).vy)
+#define QSB_VZ(p_) ((p_).vz)
+#else
+#define QSB_VX(p_) ((p_).speed * (p_).alpha)
+#define QSB_VY(p_) ((p_).speed * (p_).beta)
+#define QSB_VZ(p_) ((p_).speed * (p_).gamma)
+#endif
+
 __device__ __forceinline__ int cell_ix(const uint4& h) { return (int)(h.x & 0xffffu); }
 __device__ __forceinline__ int cell_iy(const uint4& h) { return (int)(h.x >> 16); }
 __device__ __forceinline__ int cell_iz(const uint4& h) { return (int)(h.y & 0xffffu); }
@@ -99,7 +111,10 @@ enum { kStateIdle = 0, kStateSegment = 1, kStateCollision = 2, kStateTail = 3 };
 
 struct Counters     // per-thread balance tallies, flushed once per kernel (src/Tallies.hh:36-100)
 {
-    unsigned int segments, collisions, scatters, absorbs, fissions, produced, escapes, census, lookups, slow, mismatch;
+    unsigned int segments, collisions, absorbs, fissions, produced, escapes, census;
+#if QSB_VALIDATION
+    unsigned int scatters, lookups, slow, mismatch;     // fast build: scatters = collisions - absorbs - fissions; no diagnostics
+#endif
 };
 
 // one facet plane {A,B,C,D}: two 16-byte read-only loads
@@ -264,7 +279,7 @@ __device__ __forceinline__ void load_particle_aos(const TrackArgs& a, unsigned l
 __device__ __forceinline__ void store_particle(const VaultView& v, unsigned long long i, const Particle& p, bool with_direction)
 {
     __stcg(v.x + i, p.x); __stcg(v.y + i, p.y); __stcg(v.z + i, p.z);
-    __stcg(v.vx + i, p.vx); __stcg(v.vy + i, p.vy); __stcg(v.vz + i, p.vz);
+    __stcg(v.vx + i, QSB_VX(p)); __stcg(v.vy + i, QSB_VY(p)); __stcg(v.vz + i, QSB_VZ(p));
     __stcg(v.energy + i, p.energy); __stcg(v.weight + i, p.weight); __stcg(v.ttc + i, p.ttc);
     __stcg(v.age + i, p.age); __stcg(v.nmfp + i, p.nmfp); __stcg(v.nseg + i, p.nseg);
     __stcg(v.seed + i, (unsigned long long)p.seed); __stcg(v.id + i, (unsigned long long)p.id);
@@ -389,6 +404,30 @@ __device__ __noinline__ void nearest_facet_full(const double4* __restrict__ plan
     *out_facet = nf_facet; *out_distance = nf_distance;
 }
 
+#if !QSB_VALIDATION
+// ---- nearest facet, fast build ---------------------------------------------------------------------------
+// The cell is an axis-aligned box and the fast build only has to be statistically equivalent to the reference (its
+// arithmetic already differs in the last bits), so the exit is the face with the smallest gap / |direction| and the
+// distance is that quotient -- no facet code, no plane, no triangle on the face (reflection and adjacency only need the
+// face).  A particle that rounding has left a hair outside its cell sees a negative gap and crosses with a zero-length
+// segment, which is what the reference's negative-distance fallback + clamp does (src/MCT.cc:468-476, :114).
+__device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Particle& p, int& facet, double& distance)
+{
+    const double x0 = cell_ix(p.head) * im.dx, y0 = cell_iy(p.head) * im.dy, z0 = cell_iz(p.head) * im.dz;
+    const double gx = p.alpha > 0 ? (x0 + im.dx) - p.x : p.x - x0, ax = fabs(p.alpha);
+    const double gy = p.beta  > 0 ? (y0 + im.dy) - p.y : p.y - y0, ay = fabs(p.beta);
+    const double gz = p.gamma > 0 ? (z0 + im.dz) - p.z : p.z - z0, az = fabs(p.gamma);
+    int w = -1; double gw = 0, aw = 1;
+    if (ax > 0) { w = 0; gw = gx; aw = ax; }
+    if (ay > 0 && (w < 0 || gy * aw < gw * ay)) { w = 1; gw = gy; aw = ay; }
+    if (az > 0 && (w < 0 || gz * aw < gw * az)) { w = 2; gw = gz; aw = az; }
+    if (w < 0) return false;
+    const double dw = w == 0 ? p.alpha : (w == 1 ? p.beta : p.gamma);
+    facet = 4 * (2 * w + (dw > 0 ? 0 : 1));
+    distance = fmax(gw * approx_rcp(aw), 0.0);
+    return true;
+}
+#else
 // ---- nearest facet, filtered fast path -----------------------------------------------------------------
 // Returns false when the configuration is within the safety margin of anything the reference treats with
 // tolerances (cell edges, face diagonals, the exit face itself, a particle outside its cell); the caller then
@@ -449,6 +488,8 @@ __device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Par
     return true;
 }
 
+#endif
+
 // ---- segment outcome: 0 collision, 1 facet crossing, 2 census -----------------------------------------
 __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, Counters& c)
 {
@@ -475,6 +516,7 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
 
     int nf_facet = 0; double d_facet = 0.0;
     const bool fast = im.compact && nearest_facet_fast(im, p, nf_facet, d_facet);
+#if QSB_VALIDATION
     if (!fast || (a.check_mode & 1))
     {
         int f2; double d2;
@@ -486,6 +528,18 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
         p.x = qx; p.y = qy; p.z = qz;
         nf_facet = f2; d_facet = d2;
     }
+#else
+    if (!fast)          // a mesh that is not the uniform brick grid (never built by the host model), or a zero direction vector
+    {
+        int f2; double d2;
+        double qx = p.x, qy = p.y, qz = p.z;
+        nearest_facet_full(im.planes + (size_t)p.cell * 24, im.nodes + (size_t)p.cell * 42, &qx, &qy, &qz,
+                           p.alpha, p.beta, p.gamma, p.nseg, &f2, &d2);
+        p.x = qx; p.y = qy; p.z = qz;
+        nf_facet = f2; d_facet = d2;
+        atomicAdd(&a.ctl->slow_geometry, 1ull);
+    }
+#endif
     if (force_collision) { d_facet = kHugeDouble; d_census = kHugeDouble; d_collision = kTinyDouble; }
 
     // MC_Find_Min: strict <, ties to the lower index
@@ -578,7 +632,9 @@ __device__ __forceinline__ void write_raw_child(const TrackArgs& a, unsigned lon
 {
     const VaultView& v = a.proc;
     __stcg(v.x + i, parent.x); __stcg(v.y + i, parent.y); __stcg(v.z + i, parent.z);
+#if QSB_VALIDATION
     __stcg(v.vx + i, parent.vx); __stcg(v.vy + i, parent.vy); __stcg(v.vz + i, parent.vz);
+#endif                          // fast build: the child's velocity is rebuilt by its collision tail before anything reads it
     __stcg(v.energy + i, energy_out); __stcg(v.weight + i, parent.weight); __stcg(v.ttc + i, parent.ttc);
     __stcg(v.age + i, parent.age); __stcg(v.nmfp + i, angle_out); __stcg(v.nseg + i, parent.nseg);
     __stcg(v.seed + i, (unsigned long long)child_seed); __stcg(v.id + i, (unsigned long long)child_seed);
@@ -606,6 +662,7 @@ __device__ __forceinline__ void publish_children(const TrackArgs& a, unsigned lo
 // held in registers.  Returns the flat index iso * n_react + react, or -1.
 //
 // exact chain: the reference's own sequence of subtractions, isotope after isotope.
+#if QSB_VALIDATION
 template <int NR>
 __device__ __noinline__ int select_reaction_chain(const double* __restrict__ table, int n_iso, int n_react, double current)
 {
@@ -675,6 +732,28 @@ __device__ __forceinline__ int select_reaction_periodic(const double* __restrict
     return selected;
 }
 
+#else
+// Fast build.  With identical isotopes the position inside ONE isotope's table decides the reaction, and the total is
+// n_iso times that table's sum up to rounding: the uniform number r picks isotope floor(r * n_iso) and the fraction
+// picks the reaction -- no division, no chain.  Differs from the reference's subtraction chain only where r * total
+// lies within rounding of a table boundary.
+__device__ __forceinline__ int select_reaction_fastbuild(const double* __restrict__ table, int n_iso, int n_react, double r)
+{
+    double prefix[9];
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { sum += (k < n_react) ? __ldg(table + k) : 0.0; prefix[k] = sum; }
+    const double t = r * (double)n_iso;
+    int iso = (int)t;
+    if (iso >= n_iso) iso = n_iso - 1;
+    const double rest = (t - (double)iso) * sum;
+    int first = n_react - 1;
+#pragma unroll
+    for (int k = 7; k >= 0; --k) if (k < n_react && rest < prefix[k]) first = k;
+    return iso * n_react + first;
+}
+#endif
+
 __device__ __forceinline__ int select_reaction_generic(const double* __restrict__ table, int n_total, double current)
 {
     for (int k = 0; k < n_total; ++k)
@@ -700,11 +779,16 @@ __device__ __forceinline__ int collision_head(const TrackArgs& a, Particle& p, C
     const double current = p.total_xs * r;
     int selected;
     const bool periodic = __ldg(im.mat_periodic + mat) != 0;
+#if QSB_VALIDATION
     const bool check = (a.check_mode & 2) != 0;
     if (periodic && n_react <= 3)      selected = select_reaction_periodic<3>(table, n_iso, n_react, current, p.total_xs, check, c.mismatch);
     else if (periodic && n_react <= 9) selected = select_reaction_periodic<9>(table, n_iso, n_react, current, p.total_xs, check, c.mismatch);
     else                               selected = select_reaction_generic(table, n_iso * n_react, current);
     c.lookups += (selected < 0 ? n_iso * n_react : selected + 1);
+#else
+    if (periodic && n_react <= 9) selected = select_reaction_fastbuild(table, n_iso, n_react, r);
+    else                          selected = select_reaction_generic(table, n_iso * n_react, current);
+#endif
     if (selected < 0) { atomicAdd(&a.ctl->bad_reaction, 1u); return 0; }
 
     // NuclearDataReaction::sampleCollision (src/NuclearData.cc:54-88)
@@ -738,8 +822,11 @@ __device__ __forceinline__ int collision_head(const TrackArgs& a, Particle& p, C
     }
 
     c.collisions++;
+#if QSB_VALIDATION
     if (rtype == QSB_REACT_SCATTER) c.scatters++;
-    else if (rtype == QSB_REACT_ABSORPTION) c.absorbs++;
+    else
+#endif
+    if (rtype == QSB_REACT_ABSORPTION) c.absorbs++;
     else if (rtype == QSB_REACT_FISSION) { c.fissions++; c.produced += nOut; }
 
     energy0 = energyOut[0]; angle0 = angleOut[0];
@@ -778,6 +865,16 @@ __device__ __forceinline__ void collision_tail(const TrackArgs& a, Particle& p, 
 // ---- facet crossing --------------------------------------------------------------------------------------
 __device__ __forceinline__ void reflect_particle(const DevImage& im, Particle& p)
 {
+#if !QSB_VALIDATION
+    if (im.compact)
+    {
+        // axis-aligned face: dir -= 2 (dir . n) n flips the component along the face normal (src/MCT.cc:401-429); the
+        // particle left through this face, so it is heading outwards and the reference's dot > 0 test holds
+        const int axis = p.facet >> 3;
+        if (axis == 0) p.alpha = -p.alpha; else if (axis == 1) p.beta = -p.beta; else p.gamma = -p.gamma;
+        return;
+    }
+#endif
     const double4 pl = load_plane(im.planes + (size_t)p.cell * 24 + p.facet);
     const double dot = 2.0 * (p.alpha * pl.x + p.beta * pl.y + p.gamma * pl.z);
     if (dot > 0)
@@ -801,7 +898,7 @@ __device__ __forceinline__ int flat_to_domain(const DevImage& im, int flat)
 __device__ __forceinline__ void fill_base(const DevImage& im, const Particle& p, qsb_base_particle& b)
 {
     b.coordinate[0] = p.x; b.coordinate[1] = p.y; b.coordinate[2] = p.z;
-    b.velocity[0] = p.vx; b.velocity[1] = p.vy; b.velocity[2] = p.vz;
+    b.velocity[0] = QSB_VX(p); b.velocity[1] = QSB_VY(p); b.velocity[2] = QSB_VZ(p);
     b.kinetic_energy = p.energy; b.weight = p.weight; b.time_to_census = p.ttc; b.age = p.age;
     b.num_mean_free_paths = p.nmfp; b.num_segments = p.nseg;
     b.random_number_seed = p.seed; b.identifier = p.id;
@@ -859,7 +956,7 @@ __device__ __forceinline__ void store_census_aos(const DevImage& im, qsb_base_pa
 {
     double* r = reinterpret_cast<double*>(rec);
     __stcg(r + 0, p.x); __stcg(r + 1, p.y); __stcg(r + 2, p.z);
-    __stcg(r + 3, p.vx); __stcg(r + 4, p.vy); __stcg(r + 5, p.vz);
+    __stcg(r + 3, QSB_VX(p)); __stcg(r + 4, QSB_VY(p)); __stcg(r + 5, QSB_VZ(p));
     __stcg(r + 6, p.energy); __stcg(r + 7, p.weight); __stcg(r + 8, p.ttc);
     __stcg(r + 9, p.age); __stcg(r + 10, p.nmfp); __stcg(r + 11, p.nseg);
     unsigned long long* u = reinterpret_cast<unsigned long long*>(rec);
@@ -921,7 +1018,7 @@ template <int kDummy>
 __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid_constant__ TrackArgs a)
 {
     const unsigned lane = threadIdx.x & 31u;
-    Counters c = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    Counters c = {};
     Particle p;
     unsigned long long ticket = kNoTicket;
     unsigned long long pool_next = 0, pool_end = 0;     // warp-uniform: tickets reserved by this warp, not yet handed to a lane
@@ -1125,10 +1222,15 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
 
     // flush the per-thread balance counters: warp sum, one atomic per counter per warp
     __syncwarp();
-    const unsigned int s_seg = warp_sum(c.segments), s_col = warp_sum(c.collisions), s_sca = warp_sum(c.scatters);
+    const unsigned int s_seg = warp_sum(c.segments), s_col = warp_sum(c.collisions);
     const unsigned int s_abs = warp_sum(c.absorbs), s_fis = warp_sum(c.fissions), s_pro = warp_sum(c.produced);
-    const unsigned int s_esc = warp_sum(c.escapes), s_cen = warp_sum(c.census), s_look = warp_sum(c.lookups);
-    const unsigned int s_slow = warp_sum(c.slow), s_mis = warp_sum(c.mismatch);
+    const unsigned int s_esc = warp_sum(c.escapes), s_cen = warp_sum(c.census);
+#if QSB_VALIDATION
+    const unsigned int s_sca = warp_sum(c.scatters), s_look = warp_sum(c.lookups), s_slow = warp_sum(c.slow), s_mis = warp_sum(c.mismatch);
+#else
+    // every collision of the fast build is one of the three reaction types (an undefined type would have been rejected by the host model)
+    const unsigned int s_sca = s_col - s_abs - s_fis, s_look = 0u, s_slow = 0u, s_mis = 0u;
+#endif
     if (lane == 0)
     {
         unsigned long long* b = a.ctl->balance;

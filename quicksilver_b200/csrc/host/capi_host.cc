@@ -236,6 +236,10 @@ extern "C" int qsb_mc_tracking_begin(qsb_mc* h, qsb_ctx* ctx)
         uint64_t cap = n_in + n_in / 4 + 65536;
         if (mc.processed.capacity() > cap) cap = mc.processed.capacity();
         mc.processed.clear();
+        // growing a page-locked vault costs ~0.5 s/GB (cudaHostAlloc): when it has to grow, take 1.5x so that a
+        // population that is still settling does not pay for it again every cycle
+        if (cap > mc.processed.capacity()) mc.processed.reserve(cap + cap / 2);
+        cap = mc.processed.capacity();
         mc.processed.resize(cap);
         if ((rc = qsb_stream_begin(ctx, mc.processing.data(), n_in, mc.processed.data(), cap)) != QSB_OK) return fail(rc);
         return (int)QSB_OK;
