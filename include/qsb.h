@@ -224,6 +224,22 @@ int  qsb_send_slab(qsb_ctx* ctx, int peer, void** device_ptr, uint64_t* n_record
 int  qsb_clear_sends(qsb_ctx* ctx);
 int  qsb_put_arrivals(qsb_ctx* ctx, const void* device_records, uint64_t n_records);
 uint64_t qsb_exchange_record_bytes(void);
+/* Peer exchange over NVLink / NVSwitch (replaces the per-round pack / MPI_Isend / MPI_Irecv / unpack protocol of
+ * src/MC_Particle_Buffer.cc:176-291,452-618 when all ranks drive GPUs of one node, at most QSB_MAX_PEERS of them, one domain
+ * per rank).  Each rank exports one device allocation -- a control block followed by its processing vault -- as a 64-byte
+ * CUDA IPC handle; after qsb_peer_connect with every rank's handle the tracking kernel stores a boundary-crossing particle
+ * straight into a slot of the neighbour's processing vault, where the neighbour's kernel finds it in its ticket queue while
+ * it is still tracking, and global termination (the reference's allreduce of sends/receives,
+ * src/MC_Particle_Buffer.cc:601-618) is decided on the devices.  A cycle is then ONE qsb_track call per rank, no rounds.
+ * Contract: all ranks use the same particle_capacity (qsb_peer_export returns it for the caller to compare) and call
+ * qsb_track the same number of times.  watchdog_seconds (0 = 60): a launch that has not terminated by then is abandoned
+ * on every rank and qsb_track fails. */
+#define QSB_MAX_PEERS 8
+#define QSB_PEER_HANDLE_BYTES 64
+int  qsb_peer_export(qsb_ctx* ctx, void* handle /* [QSB_PEER_HANDLE_BYTES] */, uint64_t* vault_capacity);
+int  qsb_peer_connect(qsb_ctx* ctx, const void* handles /* [n_ranks][QSB_PEER_HANDLE_BYTES], rank order */, int n_ranks,
+                      double watchdog_seconds);
+int  qsb_peer_disconnect(qsb_ctx* ctx);
 const char* qsb_last_error(qsb_ctx* ctx);
 /* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] check-mode (geometry or reaction)
  * disagreements (check mode; must be 0), [2] reaction-table entries scanned, [3] compact geometry enabled,

@@ -129,6 +129,9 @@ def _declare(lib):
         "qsb_clear_sends": (C.c_int, [vp]),
         "qsb_put_arrivals": (C.c_int, [vp, vp, C.c_uint64]),
         "qsb_exchange_record_bytes": (C.c_uint64, []),
+        "qsb_peer_export": (C.c_int, [vp, vp, u64p]),
+        "qsb_peer_connect": (C.c_int, [vp, vp, C.c_int, C.c_double]),
+        "qsb_peer_disconnect": (C.c_int, [vp]),
         "qsb_last_error": (C.c_char_p, [vp]),
         "qsb_launch_count": (C.c_uint64, [vp]),
         "qsb_get_diagnostics": (C.c_int, [vp, u64p]),

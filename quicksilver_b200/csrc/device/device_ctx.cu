@@ -185,6 +185,14 @@ struct qsb_ctx
     unsigned long long host_out_cap = 0, census_copied = 0;   // records already on their way to host_out
     size_t next_chunk = 0;
     unsigned chunk_shift = 18;                  // log2(records per streaming chunk), fixed at creation
+    // peer exchange over NVLink (qsb_peer_export / qsb_peer_connect, see include/qsb.h)
+    char* vault_base[2] = { nullptr, nullptr }; // the vaults' allocations (header + SoA arrays)
+    char* peer_block = nullptr;                 // own exported allocation: vault_base[0] (PeerControl in its header)
+    char* peer_base[kMaxPeers] = { nullptr };   // every rank's block as mapped into this process (own rank: peer_block)
+    bool peer_on = false;
+    uint32_t peer_epoch = 0;
+    unsigned long long watchdog_ns = 0;
+    PeerControl* h_peer = nullptr;              // pinned: values on their way to / back from the own control block
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
@@ -194,18 +202,15 @@ struct qsb_ctx
 
 namespace {
 
-void allocVault(qsb_ctx* c, VaultView& v, unsigned long long cap)
+// one allocation per vault: a header (the PeerControl block of the peer exchange) followed by the SoA arrays, so that the
+// whole processing vault can be exported to the other ranks with a single CUDA IPC handle
+char* allocVault(qsb_ctx* c, VaultView& v, unsigned long long cap)
 {
-    double** f64[] = { &v.x, &v.y, &v.z, &v.vx, &v.vy, &v.vz, &v.energy, &v.weight, &v.ttc, &v.age, &v.nmfp, &v.nseg,
-                       &v.dirx, &v.diry, &v.dirz };
-    for (double** p : f64) *p = devAlloc<double>(cap, c->owned);
-    v.seed = devAlloc<unsigned long long>(cap, c->owned);
-    v.id = devAlloc<unsigned long long>(cap, c->owned);
-    v.cell = devAlloc<int>(cap, c->owned);
-    v.tags = devAlloc<int4>(cap, c->owned);
-    v.ready = devAlloc<uint32_t>(cap, c->owned);
+    char* base = devAlloc<char>(vault_bytes(cap), c->owned);
+    QSB_CUDA(cudaMemset(base, 0, kVaultHeaderBytes));
+    v = vault_view(base, cap);
     QSB_CUDA(cudaMemset(v.ready, 0, cap * sizeof(uint32_t)));
-    v.capacity = cap;
+    return base;
 }
 
 void pushControl(qsb_ctx* c)
@@ -408,8 +413,9 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         // ---- vaults, slabs, tallies ----
         unsigned long long cap = c->opt.particle_capacity;
         if (cap == 0) cap = 1ull << 20;
-        allocVault(c, c->vault[0], cap);
-        allocVault(c, c->vault[1], cap);
+        cap = (cap + 31ull) & ~31ull;
+        c->vault_base[0] = allocVault(c, c->vault[0], cap);
+        c->vault_base[1] = allocVault(c, c->vault[1], cap);
         c->send_capacity = c->n_ranks > 1 ? (c->opt.send_capacity ? c->opt.send_capacity : std::max<unsigned long long>(cap / 8, 4096)) : 1;
         c->sends = devAlloc<ExchangeRecord>((size_t)c->n_ranks * c->send_capacity, c->owned);
         c->flux = devAlloc<double>(nc * ng, c->owned);
@@ -430,6 +436,8 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         check(cudaGetLastError(), "kernel attributes (is the sm_100a image loadable on this device?)");
         if (c->blocks_per_sm < 1) throw CudaFailure{ "tracking kernel cannot be resident on this device" };
         if (c->opt.blocks_per_sm > 0) c->blocks_per_sm = std::min(c->blocks_per_sm, c->opt.blocks_per_sm);
+        if (const char* e = std::getenv("QSB_BLOCKS_PER_SM"))         // occupancy experiments only
+            if (std::atoi(e) > 0) c->blocks_per_sm = std::min(c->blocks_per_sm, std::atoi(e));
         c->grid = c->sm_count * c->blocks_per_sm;
         QSB_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -449,6 +457,8 @@ int qsb_destroy(qsb_ctx* c)
     if (!c) return QSB_ERR_ARG;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    qsb_peer_disconnect(c);
+    if (c->h_peer) cudaFreeHost(c->h_peer);
     for (void* p : c->owned) cudaFree(p);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_partial) cudaFreeHost(c->h_partial);
@@ -691,6 +701,17 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.epoch = c->epoch;
         a.check_mode = ((c->opt.tracking_mode & 2) ? 1 : 0) | ((c->opt.tracking_mode & 4) ? 2 : 0);
         a.in_aos = c->d_in_aos; a.n_in = c->n_in_aos;
+        a.inflight = &c->d_ctl->inflight; a.tail = &c->d_ctl->tail;
+        a.peer_mode = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
+        for (int r = 0; r < kMaxPeers; ++r) a.peer_base[r] = c->peer_base[r];
+        if (c->peer_on)
+        {
+            if (c->proc != 0) { c->error = "peer exchange: the exported processing vault is vault 0 (keep_census is not supported with it)"; return (int)QSB_ERR_STATE; }
+            a.peer_mode = 1;
+            a.peer_epoch = ++c->peer_epoch;
+            PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
+            a.inflight = &d_peer->inflight; a.tail = &d_peer->tail;
+        }
         a.census_aos = c->streaming ? c->d_census_aos : nullptr;
         a.census_chunk_done = c->d_chunk_done; a.host_chunk_flags = c->d_chunk_flags; a.census_chunk_shift = kCensusChunkShift;
         uint32_t n_launch = 0;
@@ -700,6 +721,20 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         c->pending_inflight = 0;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->head, &c->h_ctl->head, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->inflight, &c->h_ctl->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        if (c->peer_on)
+        {
+            // the queue state of this launch, THEN the epoch that tells the other ranks it is in place (senders and the
+            // termination waves wait for it)
+            PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
+            c->h_peer->inflight = c->h_ctl->inflight;
+            c->h_peer->tail = c->h_ctl->tail;
+            c->h_peer->n_in = c->n_in_aos;
+            c->h_peer->vault_epoch = c->epoch;
+            c->h_peer->epoch = c->peer_epoch;
+            QSB_CUDA(cudaMemcpyAsync(&d_peer->inflight, &c->h_peer->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            QSB_CUDA(cudaMemcpyAsync(&d_peer->tail, &c->h_peer->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            QSB_CUDA(cudaMemcpyAsync(&d_peer->n_in, &c->h_peer->n_in, 16, cudaMemcpyHostToDevice, c->stream));        // n_in + vault_epoch + epoch
+        }
         if (c->streaming && !c->stream_input_issued)
         {
             // the DMA front must not start moving ctl->in_ready before the control block of this cycle is in place
@@ -707,7 +742,7 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             QSB_CUDA(cudaStreamWaitEvent(c->stream_in, c->ev_ctl, 0));
         }
         QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
-        if (c->h_ctl->inflight > 0)
+        if (c->h_ctl->inflight > 0 || c->peer_on)        // peer mode: every rank takes part in every launch (arrivals, termination)
         {
             if (c->opt.validation) launch_track_validation(a, c->grid, c->block, c->stream);
             else                   launch_track_fast(a, c->grid, c->block, c->stream);
@@ -732,6 +767,18 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         QSB_CUDA(cudaEventSynchronize(c->ev1));
         float ms = 0;
         QSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (c->peer_on)
+        {
+            QSB_CUDA(cudaMemcpy(c->h_peer, c->peer_block, sizeof(PeerControl), cudaMemcpyDeviceToHost));
+            c->h_ctl->inflight = c->h_peer->inflight;
+            c->h_ctl->tail = c->h_peer->tail;
+            if (c->h_peer->overflow == c->peer_epoch) c->h_ctl->overflow |= 1u;
+            if (c->h_peer->abort == c->peer_epoch)
+            {
+                c->error = "peer exchange abandoned: a rank's watchdog expired before global termination (a rank that never launched, or lost particles)";
+                return (int)QSB_ERR_INTERNAL;
+            }
+        }
         if (c->h_ctl->inflight != 0 && !c->h_ctl->overflow)
         { c->error = "tracking kernel ended with histories in flight"; return (int)QSB_ERR_INTERNAL; }
         c->consumed = std::min<unsigned long long>(c->h_ctl->tail, c->n_in_aos + a.proc.capacity);
@@ -924,6 +971,72 @@ int qsb_clear_sends(qsb_ctx* c)
         QSB_CUDA(cudaStreamSynchronize(c->stream));
         return (int)QSB_OK;
     });
+}
+
+
+int qsb_peer_export(qsb_ctx* c, void* handle, uint64_t* vault_capacity)
+{
+    if (!handle) return QSB_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == QSB_PEER_HANDLE_BYTES, "IPC handle size");
+    static_assert(kMaxPeers == QSB_MAX_PEERS, "peer limit");
+    static_assert(sizeof(PeerControl) <= kVaultHeaderBytes, "vault header");
+    return guarded(c, [&]() {
+        if (c->im.n_domains != 1) { c->error = "peer exchange needs one domain per rank"; return (int)QSB_ERR_STATE; }
+        if (!c->peer_block)
+        {
+            c->peer_block = c->vault_base[0];
+            QSB_CUDA(cudaMallocHost((void**)&c->h_peer, sizeof(PeerControl)));
+            std::memset(c->h_peer, 0, sizeof(PeerControl));
+        }
+        cudaIpcMemHandle_t h;
+        QSB_CUDA(cudaIpcGetMemHandle(&h, c->peer_block));
+        std::memcpy(handle, &h, sizeof h);
+        if (vault_capacity) *vault_capacity = c->vault[0].capacity;
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_peer_connect(qsb_ctx* c, const void* handles, int n_ranks, double watchdog_seconds)
+{
+    if (!handles) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->peer_block) { c->error = "qsb_peer_connect before qsb_peer_export"; return (int)QSB_ERR_STATE; }
+        if (n_ranks != c->n_ranks || n_ranks > kMaxPeers)
+        { c->error = "qsb_peer_connect: rank count must equal the image's and be at most QSB_MAX_PEERS"; return (int)QSB_ERR_ARG; }
+        if (c->peer_on) return (int)QSB_OK;
+        for (int r = 0; r < n_ranks; ++r)
+        {
+            if (r == c->my_rank) { c->peer_base[r] = c->peer_block; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)handles + (size_t)r * QSB_PEER_HANDLE_BYTES, sizeof h);
+            void* p = nullptr;
+            const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+            {
+                cudaGetLastError();
+                for (int q = 0; q < r; ++q) if (q != c->my_rank && c->peer_base[q]) { cudaIpcCloseMemHandle(c->peer_base[q]); c->peer_base[q] = nullptr; }
+                c->error = std::string("cudaIpcOpenMemHandle failed for rank ") + std::to_string(r) + ": " + cudaGetErrorString(e);
+                return (int)QSB_ERR_CUDA;
+            }
+            c->peer_base[r] = (char*)p;
+        }
+        c->watchdog_ns = (unsigned long long)((watchdog_seconds > 0 ? watchdog_seconds : 60.0) * 1e9);
+        c->peer_on = true;
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_peer_disconnect(qsb_ctx* c)
+{
+    if (!c) return QSB_ERR_ARG;
+    cudaSetDevice(c->device);
+    for (int r = 0; r < kMaxPeers; ++r)
+    {
+        if (r != c->my_rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+        c->peer_base[r] = nullptr;
+    }
+    c->peer_on = false;
+    return QSB_OK;
 }
 
 } // extern "C"

@@ -105,6 +105,55 @@ struct DevControl
     unsigned long long send_count[64];  // per peer rank
 };
 
+// Peer exchange over NVLink (one process per GPU, all GPUs of one NVSwitch domain).  Every rank exports ONE allocation
+// through CUDA IPC: this control block followed by its processing vault (all SoA arrays in one allocation, see
+// vault_view).  A tracking kernel whose particle crosses onto a peer's domain takes a slot of the PEER's processing vault
+// with a system-scope atomic on the peer's tail counter, raises the peer's in-flight count, stores the particle into the
+// peer's SoA arrays through NVLink and releases the slot's ready word -- to the peer's tracking warps the arrival looks
+// like a fission secondary that appeared in their ticket queue; nothing on the receiving side copies or converts.
+// `sent` / `received` are monotonic over the life of the context; `tail`, `inflight`, `n_in`, `vault_epoch` belong to the
+// launch named by `epoch` (the host writes them, then `epoch`, in stream order before the launch; a sender waits for the
+// peer's epoch before it touches them).  Global termination is decided on the devices: peer_service_loop in track_kernels.cu.
+constexpr int kMaxPeers = 8;
+struct PeerControl
+{
+    unsigned long long sent;            // boundary particles this GPU has started to deposit elsewhere (local atomics)
+    unsigned long long pad0[31];
+    unsigned long long received;        // deposits counted into this GPU's in-flight count (remote atomics, after `inflight`)
+    unsigned long long pad1[31];
+    unsigned long long inflight;        // histories queued or running on this GPU (the kernel's in-flight counter in peer mode)
+    unsigned long long pad2[31];
+    unsigned long long tail;            // tickets allocated (the kernel's queue tail in peer mode; remote senders add to it)
+    unsigned long long pad3[31];
+    unsigned long long n_in;            // this launch: tickets below n_in are streamed host records, SoA slot = ticket - n_in
+    unsigned int vault_epoch;           // this launch: value of a slot's ready word once it is fully written
+    unsigned int epoch;                 // number of the peer-mode launch the words above belong to
+    unsigned int done;                  // == epoch: this GPU has seen global termination of that launch
+    unsigned int abort;                 // == epoch: some GPU gave up (watchdog); everybody leaves
+    unsigned int overflow;              // == epoch: a sender found this GPU's processing vault full
+    unsigned int pad4[25];
+};
+static_assert(sizeof(PeerControl) == 1152, "PeerControl layout");
+constexpr size_t kVaultHeaderBytes = 2048;     // PeerControl sits at the head of the processing vault's allocation
+
+// the SoA arrays of a vault inside one allocation: 17 eight-byte arrays, tags, cell, ready (capacity is a multiple of 32)
+__host__ __device__ inline VaultView vault_view(char* base, unsigned long long cap)
+{
+    VaultView v;
+    double* d = reinterpret_cast<double*>(base + kVaultHeaderBytes);
+    v.x = d; v.y = d + cap; v.z = d + 2 * cap; v.vx = d + 3 * cap; v.vy = d + 4 * cap; v.vz = d + 5 * cap;
+    v.energy = d + 6 * cap; v.weight = d + 7 * cap; v.ttc = d + 8 * cap; v.age = d + 9 * cap; v.nmfp = d + 10 * cap; v.nseg = d + 11 * cap;
+    v.dirx = d + 12 * cap; v.diry = d + 13 * cap; v.dirz = d + 14 * cap;
+    v.seed = reinterpret_cast<unsigned long long*>(d + 15 * cap);
+    v.id = reinterpret_cast<unsigned long long*>(d + 16 * cap);
+    v.tags = reinterpret_cast<int4*>(d + 17 * cap);
+    v.cell = reinterpret_cast<int*>(d + 19 * cap);
+    v.ready = reinterpret_cast<uint32_t*>(v.cell + cap);
+    v.capacity = cap;
+    return v;
+}
+inline size_t vault_bytes(unsigned long long cap) { return kVaultHeaderBytes + (size_t)cap * (19 * 8 + 4 + 4); }
+
 struct TrackArgs
 {
     DevImage im;
@@ -128,6 +177,14 @@ struct TrackArgs
     unsigned int census_chunk_shift;
     uint32_t epoch;                     // value of a slot's ready word once it is fully written this cycle
     int check_mode;                     // bit 0: evaluate both geometry paths, bit 1: both reaction selections; count disagreements
+    unsigned long long* inflight;       // the in-flight counter and the queue tail: ctl's, or the exported PeerControl's in peer mode
+    unsigned long long* tail;
+    // peer exchange (peer_mode != 0): base of every rank's exported allocation (own rank: the local pointer); every rank's
+    // processing vault has this rank's capacity
+    int peer_mode, my_rank;
+    uint32_t peer_epoch;
+    char* peer_base[kMaxPeers];
+    unsigned long long watchdog_ns;     // give up (abort everywhere) when a launch has not terminated after this long
 };
 
 // launchers implemented twice in track_kernels.cu (validation: --fmad=false + strict math; fast)

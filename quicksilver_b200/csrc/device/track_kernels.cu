@@ -58,6 +58,9 @@ constexpr unsigned kRefill = QSB_REFILL;  // idle lanes a warp lets gather befor
 #ifndef QSB_OPT_PREFETCH_L2
 #define QSB_OPT_PREFETCH_L2 1
 #endif
+#ifndef QSB_OPT_PREFETCH_ADJ
+#define QSB_OPT_PREFETCH_ADJ 0
+#endif
 #ifndef QSB_OPT_SPARE
 #define QSB_OPT_SPARE 1
 #endif
@@ -423,7 +426,13 @@ __device__ __forceinline__ bool nearest_facet_fast(const DevImage& im, const Par
     if (az > 0 && (w < 0 || gz * aw < gw * az)) { w = 2; gw = gz; aw = az; }
     if (w < 0) return false;
     const double dw = w == 0 ? p.alpha : (w == 1 ? p.beta : p.gamma);
-    facet = 4 * (2 * w + (dw > 0 ? 0 : 1));
+    const int face = 2 * w + (dw > 0 ? 0 : 1);
+    facet = 4 * face;
+#if QSB_OPT_PREFETCH_ADJ
+    // every other segment ends on this face: start pulling the neighbour's record towards L1 now (the adjacency word sits in
+    // the sectors of this cell's record that are already there), instead of a dependent miss after the crossing
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(im.cells + __ldg(im.cells[p.cell].adj + face)));
+#endif
     distance = fmax(gw * approx_rcp(aw), 0.0);
     return true;
 }
@@ -907,8 +916,9 @@ __device__ __forceinline__ void fill_base(const DevImage& im, const Particle& p,
     b.domain = d; b.cell = p.cell - __ldg(im.domain_cell_offset + d);
 }
 
-// returns true when the particle keeps tracking
-__device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particle& p, Counters& c)
+// returns 1 when the particle keeps tracking, 0 when its history ends on this GPU, 2 when it ends here and the particle
+// still has to be deposited in a peer's ring (peer mode; done by send_flush in the warp's next service phase)
+__device__ __forceinline__ int facet_crossing_event(const TrackArgs& a, Particle& p, Counters& c)
 {
     const DevImage& im = a.im;
     const int face = p.facet >> 2;
@@ -918,24 +928,25 @@ __device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particl
         p.cell = __ldg(im.cells[p.cell].adj + face);
         p.head = load_cell_head(im, p.cell);
         p.last_event = QSB_EV_FACET_TRANSIT;
-        return true;
+        return 1;
     }
     if (event == QSB_ADJ_REFLECT)
     {
         p.last_event = QSB_EV_REFLECTION;
         reflect_particle(im, p);
-        return true;
+        return 1;
     }
     if (event == QSB_ADJ_ESCAPE)
     {
         p.last_event = QSB_EV_ESCAPE;
         p.species = -1;
         c.escapes++;
-        return false;
+        return 0;
     }
     if (event == QSB_ADJ_TRANSIT_OFF)
     {
         p.last_event = QSB_EV_COMMUNICATION;
+        if (a.peer_mode) return 2;
         const size_t k = (size_t)p.cell * 6 + face;
         const int rank = __ldg(im.face_nbr_rank + k);
         const unsigned long long slot = atomicAdd(&a.ctl->send_count[rank], 1ull);
@@ -946,9 +957,163 @@ __device__ __forceinline__ bool facet_crossing_event(const TrackArgs& a, Particl
         rec.p.cell = __ldg(im.face_adj_cell + k);
         rec.dir[0] = p.alpha; rec.dir[1] = p.beta; rec.dir[2] = p.gamma;
         a.sends[(size_t)rank * a.send_capacity + slot] = rec;
-        return false;
+        return 0;
     }
-    return false;
+    return 0;
+}
+
+// ---- peer exchange over NVLink ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// relaxed system-scope loads: served by the owning GPU's L2 (never this SM's L1), no fence and -- unlike ld.acquire --
+// no invalidation of the SM's L1, which holds the cell records and cross-section tables of every warp on it
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ PeerControl* peer_control(const TrackArgs& a, int rank) { return reinterpret_cast<PeerControl*>(a.peer_base[rank]); }
+
+// what a block knows about the peers' current launch (filled once per block at kernel start, see track_kernel)
+struct PeerLaunch { unsigned long long n_in; unsigned int vault_epoch; unsigned int pad; };
+
+// Deposit the particles of all lanes whose history just left this GPU's domain straight into the neighbours' processing
+// vaults (the reference packs them into per-neighbour MPI buffers and unpacks them on the other side,
+// src/MC_Facet_Crossing_Event.cc:49-67 + src/MC_Particle_Buffer.cc:258-291,452-502).  Runs converged in the service phase,
+// BEFORE the warp retires those histories from the local in-flight count.  Order of the counter updates (what the
+// termination test relies on): own `sent` (performed: its value has come back) -> peer's `inflight` and `tail` (performed)
+// -> peer's `received` -> ... -> own in-flight count drops.  No fence on this path except the release of the slot's
+// ready word (fences with acquire semantics would invalidate this SM's L1 on every crossing).
+__device__ __forceinline__ void send_flush(const TrackArgs& a, const PeerLaunch* launch, const Particle& p, bool pending)
+{
+    if (pending)
+    {
+        const DevImage& im = a.im;
+        const int face = p.facet >> 2;
+        const size_t k = (size_t)p.cell * 6 + face;
+        const int rank = __ldg(im.face_nbr_rank + k);
+        atomicAdd(&a.ctl->send_count[rank], 1ull);                                   // statistics only
+        PeerControl* me = peer_control(a, a.my_rank);
+        PeerControl* pc = peer_control(a, rank);
+        const unsigned long long sent_before = atomicAdd(&me->sent, 1ull);
+        // the remote atomics are issued only once the local one has returned (address dependency on its value)
+        unsigned long long* remote_inflight = &pc->inflight + (sent_before & 0ull);
+        atomicAdd_system(remote_inflight, 1ull);
+        const unsigned long long ticket = atomicAdd_system(&pc->tail, 1ull);
+        asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&pc->received + (ticket & 0ull)), "l"(1ull) : "memory");
+        const unsigned long long slot = ticket - launch[rank].n_in;
+        if (slot >= a.proc.capacity)
+        {
+            st_release_sys(&pc->overflow, a.peer_epoch);           // the peer's host reports it; the particle is dropped
+            atomicAdd_system(&pc->inflight, 0ull - 1ull);
+        }
+        else
+        {
+            const VaultView v = vault_view(a.peer_base[rank], a.proc.capacity);
+            Particle q = p;
+            q.cell = __ldg(im.face_adj_cell + k);                   // the neighbour's flat cell index (one domain per rank)
+            store_particle(v, slot, q, true);
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(v.ready + slot), "r"(launch[rank].vault_epoch) : "memory");
+        }
+    }
+    __syncwarp();
+}
+
+// One wave of the termination test (Mattern's four-counter method): lane r reads rank r's control block through NVLink --
+// launch epoch, `received`, in-flight count, `sent`, in that order.  passive = every rank has started this launch and had
+// nothing queued or running when its in-flight count was read (after its `received`).
+__device__ __forceinline__ bool peer_wave(const TrackArgs& a, unsigned lane, unsigned long long& received, unsigned long long& sent, bool& aborted)
+{
+    bool passive = true, ab = false;
+    received = 0; sent = 0;
+    if ((int)lane < a.im.n_ranks)
+    {
+        const PeerControl* pc = peer_control(a, (int)lane);
+        const unsigned int e = ld_acquire_sys(&pc->epoch);
+        received = ld_acquire_sys(&pc->received);
+        const unsigned long long inf = ld_acquire_sys(&pc->inflight);
+        sent = ld_acquire_sys(&pc->sent);
+        ab = ld_acquire_sys(&pc->abort) == a.peer_epoch;
+        passive = e == a.peer_epoch && inf == 0ull;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        received += __shfl_xor_sync(kFullMask, received, d);
+        sent += __shfl_xor_sync(kFullMask, sent, d);
+    }
+    aborted = __any_sync(kFullMask, ab);
+    return __all_sync(kFullMask, passive);
+}
+
+// The service warp of a GPU in peer mode (warp 0 of block 0; it tracks nothing) decides global termination.  A rank is
+// passive when its in-flight count is zero; a passive rank becomes active only by a deposit, and a deposit is counted in
+// the sender's `sent` before, and in the receiver's `received` after, it has raised the receiver's in-flight count.  When
+// this GPU is passive the warp takes two waves over all ranks; if every rank was passive in both and the totals satisfy
+// received(wave 1) == sent(wave 1) == received(wave 2) == sent(wave 2), no deposit was under way and no rank was active
+// at the end of the first wave, and termination is stable.  `done` then releases the idle tracking warps.  A launch that
+// has not terminated after watchdog_ns raises `abort` on every rank instead.
+__device__ __noinline__ void peer_service_loop(const TrackArgs& a, unsigned lane)
+{
+    PeerControl* me = peer_control(a, a.my_rank);
+    const unsigned long long t_start = global_timer_ns();
+    unsigned sleep = 500;
+    for (;;)
+    {
+        unsigned long long inflight = 1;
+        if (lane == 0) inflight = ld_relaxed_sys(&me->inflight);
+        inflight = __shfl_sync(kFullMask, inflight, 0);
+        bool aborted = ld_relaxed_sys(&me->abort) == a.peer_epoch;
+        if (!aborted && inflight == 0ull)
+        {
+            unsigned long long r1, s1, r2 = 0, s2 = 0;
+            bool ab1 = false, ab2 = false;
+            const bool passive1 = peer_wave(a, lane, r1, s1, ab1);
+            const bool passive2 = passive1 && r1 == s1 && peer_wave(a, lane, r2, s2, ab2);
+            aborted = ab1 || ab2;
+            if (passive2 && r2 == r1 && s2 == r1)
+            {
+                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&me->done), "r"(a.peer_epoch) : "memory");
+                return;
+            }
+        }
+        if (aborted || global_timer_ns() - t_start > a.watchdog_ns) break;
+        __nanosleep(sleep);
+        if (sleep < 4000) sleep *= 2;
+        if (inflight != 0ull) sleep = 4000;     // still tracking locally: nothing to decide yet
+    }
+    if ((int)lane < a.im.n_ranks) st_release_sys(&peer_control(a, (int)lane)->abort, a.peer_epoch);      // tell everybody, ourselves included
 }
 
 // census record as the host wants it: MC_Base_Particle layout, 17 eight-byte L2 stores
@@ -1035,6 +1200,28 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
     bool spare_valid = false;
     int state = kStateIdle;                             // what this lane's particle needs next (kState*)
     unsigned retired = 0;                               // warp-uniform: histories finished since the last service phase
+    bool send_pending = false;                          // peer mode: history left for a neighbour's domain, record still in registers
+
+    // peer mode: before anything can be deposited on a peer, that peer's control words for THIS launch must be in place
+    // (its host writes them, then the epoch).  Each block waits for every peer once and keeps what senders need.
+    __shared__ PeerLaunch s_launch[kMaxPeers];
+    if (a.peer_mode)
+    {
+        if ((int)threadIdx.x < a.im.n_ranks)
+        {
+            const PeerControl* pc = peer_control(a, (int)threadIdx.x);
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(&pc->epoch) != a.peer_epoch && global_timer_ns() - t0 < a.watchdog_ns) __nanosleep(500);
+            s_launch[threadIdx.x].n_in = ld_relaxed_sys(&pc->n_in);
+            s_launch[threadIdx.x].vault_epoch = ld_relaxed_sys(&pc->vault_epoch);
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && threadIdx.x < 32u)
+        {
+            peer_service_loop(a, lane);                 // this GPU's service warp: global termination, tracks nothing
+            return;
+        }
+    }
 
     for (;;)
     {
@@ -1050,7 +1237,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
         {
             // retire the histories that finished since the last service phase: one reduction per warp.  Secondaries were
             // counted before they became visible, so inflight reaches 0 only when nothing is queued or running.
-            if (retired && lane == 0) atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)retired);
+            if (__builtin_expect(a.peer_mode != 0, 0) && __any_sync(kFullMask, send_pending)) { send_flush(a, s_launch, p, send_pending); send_pending = false; }
+            if (retired && lane == 0) atomicAdd(a.inflight, 0ull - (unsigned long long)retired);
             retired = 0u;
             census_flush(a, p, census_pending, lane, census_base, census_count, census_leader, census_rank);
             census_pending = false; census_count = 0u;
@@ -1116,9 +1304,19 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             }
             if (__ballot_sync(kFullMask, state != kStateIdle) == 0u)
             {
-                // idle warp: the cycle is over when no history is queued or running anywhere on this GPU
+                // idle warp: the cycle is over when no history is queued or running anywhere on this GPU -- or, in peer
+                // mode, anywhere on any GPU (the service warp's verdict)
                 unsigned long long inflight = 1;
-                if (lane == 0) inflight = *((volatile unsigned long long*)&a.ctl->inflight);
+                if (lane == 0)
+                {
+                    if (!a.peer_mode) inflight = *((volatile unsigned long long*)a.inflight);
+                    else
+                    {
+                        const PeerControl* me = peer_control(a, a.my_rank);
+                        const unsigned done = *((volatile const unsigned int*)&me->done), abrt = *((volatile const unsigned int*)&me->abort);
+                        inflight = (done == a.peer_epoch || abrt == a.peer_epoch) ? 0ull : 1ull;
+                    }
+                }
                 inflight = __shfl_sync(kFullMask, inflight, 0);
                 if (inflight == 0ull) break;
                 __nanosleep(backoff);
@@ -1158,8 +1356,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                 unsigned long long base = 0;
                 if (lane == 0)
                 {
-                    base = atomicAdd(&a.ctl->tail, (unsigned long long)total);
-                    atomicAdd(&a.ctl->inflight, (unsigned long long)total);
+                    base = atomicAdd(a.tail, (unsigned long long)total);
+                    atomicAdd(a.inflight, (unsigned long long)total);
                 }
                 base = __shfl_sync(kFullMask, base, 0) - a.n_in;     // tickets below n_in are the streamed host records
                 if (n_child)
@@ -1168,7 +1366,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                     if (first + n_child > a.proc.capacity)
                     {
                         atomicOr(&a.ctl->overflow, 1u);
-                        atomicAdd(&a.ctl->inflight, 0ull - (unsigned long long)n_child);
+                        atomicAdd(a.inflight, 0ull - (unsigned long long)n_child);
                     }
                     else
                     {
@@ -1196,7 +1394,11 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                 c.segments++;
                 p.nseg += 1.;
                 if (outcome == 0) state = kStateCollision;
-                else if (outcome == 1) { if (!facet_crossing_event(a, p, c)) { state = kStateIdle; finished = true; } }
+                else if (outcome == 1)
+                {
+                    const int go = facet_crossing_event(a, p, c);
+                    if (go != 1) { state = kStateIdle; finished = true; send_pending = go == 2; }
+                }
                 else { census_pending = true; c.census++; state = kStateIdle; finished = true; }     // stored in the next service phase
             }
             // census slots for the histories that just ended: one atomic per warp, its result is not read before the service phase

@@ -107,6 +107,26 @@ class DeviceContext:
     def put_arrivals(self, device_ptr, n):
         self._check(self._lib.qsb_put_arrivals(self._h, C.c_void_p(device_ptr), int(n)))
 
+    PEER_HANDLE_BYTES = 64
+    MAX_PEERS = 8
+
+    def peer_export(self):
+        """qsb_peer_export: (64-byte CUDA IPC handle of this rank's exchange ring, ring capacity in records)."""
+        buf = (C.c_ubyte * self.PEER_HANDLE_BYTES)()
+        cap = C.c_uint64()
+        self._check(self._lib.qsb_peer_export(self._h, buf, C.byref(cap)))
+        return bytes(buf), cap.value
+
+    def peer_connect(self, handles, watchdog_seconds=0.0):
+        """qsb_peer_connect: `handles` = every rank's handle in rank order (bytes, n_ranks * 64)."""
+        raw = bytes(handles)
+        assert len(raw) == self.n_ranks * self.PEER_HANDLE_BYTES
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._check(self._lib.qsb_peer_connect(self._h, buf, self.n_ranks, float(watchdog_seconds)))
+        self.peer_mode = True
+
+    peer_mode = False
+
     def diagnostics(self):
         out = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.qsb_get_diagnostics(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))

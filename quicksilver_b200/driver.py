@@ -30,6 +30,10 @@ class DeviceBackend:
     def __init__(self, ctx, torch_device):
         self.ctx, self.torch_device = ctx, torch_device
 
+    @property
+    def peer_mode(self):
+        return self.ctx.peer_mode
+
     def begin(self, vault):
         self.ctx.cycle_begin()
         self.ctx.put_particles(vault)
@@ -72,11 +76,54 @@ class DeviceBackend:
         return self.ctx.get_census(), self.ctx.get_balance(), self.ctx.scalar_flux_sum()
 
 
+def connect_peers(ctx, dist, rank, world, torch_device, watchdog_seconds=0.0):
+    """Wire the ranks' exchange rings together over NVLink: every rank exports its ring as a CUDA IPC handle, the handles
+    are all-gathered, every rank maps the others' rings (qsb_peer_connect).  All ranks agree on the outcome: True = the
+    tracking kernels exchange boundary particles themselves (one launch per cycle), False = NCCL rounds (exchange_rounds)."""
+    import torch
+    if world < 2 or world > ctx.MAX_PEERS:
+        return False
+    ok, mine, cap = 1, bytes(ctx.PEER_HANDLE_BYTES), 0
+    try:
+        mine, cap = ctx.peer_export()
+    except Exception:
+        ok = 0
+    caps = torch.tensor([cap, -cap], dtype=torch.int64, device=torch_device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+    if int(caps[0].item()) != -int(caps[1].item()):      # max != min: the ranks' vaults differ in capacity
+        ok = 0
+    is_cuda = dist.get_backend() == "nccl"
+    dev = torch_device if is_cuda else "cpu"
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return False
+    local = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+    try:
+        ctx.peer_connect(handles, watchdog_seconds)
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        ctx._lib.qsb_peer_disconnect(ctx._h)
+        ctx.peer_mode = False
+        return False
+    return True
+
+
 def exchange_rounds(backend, dist, rank, world, max_rounds=100000):
     """Track to exhaustion, swap boundary particles, repeat until no rank sent anything.
-    Returns (rounds, records sent by this rank)."""
+    Returns (rounds, records sent by this rank).  With the rings wired over NVLink (connect_peers) the kernels do the
+    exchange and the termination test themselves: one launch, one "round"."""
     import torch
     sent_total, rounds = 0, 0
+    if getattr(backend, "peer_mode", False):
+        stats = backend.track()
+        return 1, int(stats.n_sent)
     while True:
         backend.track()
         rounds += 1
@@ -140,6 +187,13 @@ class Simulation:
         self.ctx = device_mod.DeviceContext(self.mc.image, self.mc.get_double("dt"), device=device, validation=validation,
                                             particle_capacity=particle_capacity, send_capacity=send_capacity)
         self.backend = DeviceBackend(self.ctx, self.torch_device)
+        # boundary particles: device-to-device rings over NVLink where available ("peer"), else NCCL send/recv rounds
+        import os
+        want = os.environ.get("QSB_EXCHANGE", "peer")
+        self.exchange = "nccl"
+        if world > 1 and want == "peer" and dist is not None and dist.get_backend() == "nccl":
+            if connect_peers(self.ctx, dist, rank, world, self.torch_device, float(os.environ.get("QSB_PEER_WATCHDOG_S", "0"))):
+                self.exchange = "peer"
 
     def _allreduce(self, arr):
         import torch
@@ -287,7 +341,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
               "kernels": "fast" if args.fast else "validation", "timing": "inputs larger than L2 (vault %.0f MB, mesh %.0f MB per GPU); value: %s; e2e: wall clock around the "
               "drop-in call with host vaults" % (w["particles"] * 160 / 1e6, n ** 3 * 1.2e-3,
               "CUDA events on the tracking stream" if world == 1 else "host clock between device syncs + barriers around the exchange rounds, max over ranks"),
-              "scale": args.scale}
+              "scale": args.scale, "exchange": getattr(sim, "exchange", "none") if world > 1 else "none"}
     out = {"segments_total": segments, "kernel_seconds_max": kernel_max, "e2e_seconds_max": e2e_max,
            "segments_rank0": segments / world, "kernel_seconds_rank0": kernel_s, "config": config, "clocks": clocks,
            "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),

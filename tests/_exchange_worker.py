@@ -44,7 +44,7 @@ def main():
         census["domain"] = 0
         np.save(os.path.join(out_dir, "census_c%d_r%d.npy" % (c, rank)), census)
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
-        json.dump({"rows": rows, "info": info}, f)
+        json.dump({"rows": rows, "info": info, "exchange": getattr(sim, "exchange", "rounds")}, f)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -42,9 +42,12 @@ def _single_rank_strict(argv, cycles):
     return rows, censuses
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("deck_name,grid,n,per_cell", [("CTS2", (2, 1, 1), 8, 10), ("Coral2_P1", (2, 2, 1), 6, 40),
                                                          ("Coral2_P2", (2, 2, 2), 4, 40)])
-def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_cell):
+def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_cell, exchange):
+    """exchange = "peer": the kernels deposit boundary particles in each other's rings over NVLink and decide termination
+    on the devices (one launch per cycle); "nccl": per-round slabs moved with NCCL send/recv."""
     gx, gy, gz = grid
     world = gx * gy * gz
     if _gpu_count() < world:
@@ -64,10 +67,13 @@ def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_c
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(H.ROOT, "tests", "_exchange_worker.py"), str(out), str(cycles)] + argvN
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
-                         env=dict(os.environ, QSB_TEST_BACKEND="device"))
+                         env=dict(os.environ, QSB_TEST_BACKEND="device", QSB_EXCHANGE=exchange, QSB_PEER_WATCHDOG_S="20"))
     assert res.returncode == 0, res.stdout[-3000:]
     ranks = [json.load(open(out / ("rank%d.json" % r))) for r in range(world)]
     assert sum(i["sent"] for r in ranks for i in r["info"]) > 0
+    assert all(r["exchange"] == exchange for r in ranks), [r["exchange"] for r in ranks]
+    if exchange == "peer":
+        assert all(i["rounds"] == 1 for r in ranks for i in r["info"])
     for c in range(cycles):
         got, want = ranks[0]["rows"][c], want_rows[c]
         assert got[:13] == want[:13], "cycle %d: %s != %s" % (c, got[:13], want[:13])
