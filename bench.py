@@ -188,6 +188,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": result.get("traffic"), "peak_source": peak_src, "kernel": "track_kernel",
                          "algorithmic_bytes_per_segment": w["b_seg"]},
+            "tracking_ms_per_step_rank0": result["tracking_ms_per_step_rank0"],
             "balance_check": result["balance_check"]}
     if args.cpu_baseline and world == 1:
         try:

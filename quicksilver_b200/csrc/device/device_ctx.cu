@@ -773,6 +773,15 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             c->h_ctl->inflight = c->h_peer->inflight;
             c->h_ctl->tail = c->h_peer->tail;
             if (c->h_peer->overflow == c->peer_epoch) c->h_ctl->overflow |= 1u;
+            static const bool trace_peer = std::getenv("QSB_TRACE") != nullptr;
+            if (trace_peer)
+            {
+                std::fprintf(stderr, "[qsb] rank %d peer launch %u: kernel %.3f ms, first idle after %.3f ms, global termination seen after %.3f ms, tail %llu; "
+                             "send_advance: %llu calls, %.1f Mcycles over all warps; start-up wait %.3f ms\n",
+                             c->my_rank, c->peer_epoch, ms, c->h_peer->first_idle_ns * 1e-6, c->h_peer->done_ns * 1e-6, c->h_peer->tail,
+                             c->h_peer->send_calls, c->h_peer->send_cycles * 1e-6, c->h_peer->startup_wait_ns * 1e-6);
+                QSB_CUDA(cudaMemset(&reinterpret_cast<PeerControl*>(c->peer_block)->send_cycles, 0, 16));
+            }
             if (c->h_peer->abort == c->peer_epoch)
             {
                 c->error = "peer exchange abandoned: a rank's watchdog expired before global termination (a rank that never launched, or lost particles)";
@@ -781,6 +790,10 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         }
         if (c->h_ctl->inflight != 0 && !c->h_ctl->overflow)
         { c->error = "tracking kernel ended with histories in flight"; return (int)QSB_ERR_INTERNAL; }
+        {
+            static const bool trace_track = std::getenv("QSB_TRACE") != nullptr;
+            if (trace_track && !c->peer_on) std::fprintf(stderr, "[qsb] rank %d track: kernel %.3f ms, tail %llu\n", c->my_rank, ms, c->h_ctl->tail);
+        }
         c->consumed = std::min<unsigned long long>(c->h_ctl->tail, c->n_in_aos + a.proc.capacity);
         if (stats)
         {
@@ -1021,7 +1034,7 @@ int qsb_peer_connect(qsb_ctx* c, const void* handles, int n_ranks, double watchd
             c->peer_base[r] = (char*)p;
         }
         c->watchdog_ns = (unsigned long long)((watchdog_seconds > 0 ? watchdog_seconds : 60.0) * 1e9);
-        c->peer_on = true;
+        c->peer_on = std::getenv("QSB_DEBUG_PEER_MAP_ONLY") == nullptr;      // experiment: mappings in place, exchange left to the caller
         return (int)QSB_OK;
     });
 }

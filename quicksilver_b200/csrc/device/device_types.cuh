@@ -66,9 +66,11 @@ struct VaultView
     double *x, *y, *z, *vx, *vy, *vz, *energy, *weight, *ttc, *age, *nmfp, *nseg;
     double *dirx, *diry, *dirz;
     unsigned long long *seed, *id;
+    unsigned long long *check;      // peer deposits only: XOR of the record's words and a per-launch salt (the record validates itself)
     int *cell;
     int4 *tags;                     // {last_event, num_collisions, breed, species}
-    uint32_t *ready;                // == epoch once the slot is fully written (processing vault only)
+    uint32_t *ready;                // == epoch once the slot is fully written (processing vault only); epoch | kArrivalBit: a
+                                    // peer's deposit is on its way into the slot -- complete when `check` matches the record
     unsigned long long capacity;
 };
 
@@ -117,7 +119,7 @@ struct DevControl
 constexpr int kMaxPeers = 8;
 struct PeerControl
 {
-    unsigned long long sent;            // boundary particles this GPU has started to deposit elsewhere (local atomics)
+    unsigned long long sent;            // deposits started TOWARDS this GPU (remote atomics, while the sender still counts the history)
     unsigned long long pad0[31];
     unsigned long long received;        // deposits counted into this GPU's in-flight count (remote atomics, after `inflight`)
     unsigned long long pad1[31];
@@ -131,12 +133,18 @@ struct PeerControl
     unsigned int done;                  // == epoch: this GPU has seen global termination of that launch
     unsigned int abort;                 // == epoch: some GPU gave up (watchdog); everybody leaves
     unsigned int overflow;              // == epoch: a sender found this GPU's processing vault full
-    unsigned int pad4[25];
+    unsigned int pad4;
+    unsigned long long first_idle_ns;   // diagnostics of the last launch: kernel start -> this GPU first had nothing queued or running,
+    unsigned long long done_ns;         //                                  kernel start -> global termination seen
+    unsigned long long send_cycles;     //   SM cycles warps spent inside send_advance, summed over warps; calls; start-up wait cycles (block 0)
+    unsigned long long send_calls;
+    unsigned long long startup_wait_ns;
+    unsigned int pad5[14];
 };
 static_assert(sizeof(PeerControl) == 1152, "PeerControl layout");
 constexpr size_t kVaultHeaderBytes = 2048;     // PeerControl sits at the head of the processing vault's allocation
 
-// the SoA arrays of a vault inside one allocation: 17 eight-byte arrays, tags, cell, ready (capacity is a multiple of 32)
+// the SoA arrays of a vault inside one allocation: 18 eight-byte arrays, tags, cell, ready (capacity is a multiple of 32)
 __host__ __device__ inline VaultView vault_view(char* base, unsigned long long cap)
 {
     VaultView v;
@@ -146,13 +154,16 @@ __host__ __device__ inline VaultView vault_view(char* base, unsigned long long c
     v.dirx = d + 12 * cap; v.diry = d + 13 * cap; v.dirz = d + 14 * cap;
     v.seed = reinterpret_cast<unsigned long long*>(d + 15 * cap);
     v.id = reinterpret_cast<unsigned long long*>(d + 16 * cap);
-    v.tags = reinterpret_cast<int4*>(d + 17 * cap);
-    v.cell = reinterpret_cast<int*>(d + 19 * cap);
+    v.check = reinterpret_cast<unsigned long long*>(d + 17 * cap);
+    v.tags = reinterpret_cast<int4*>(d + 18 * cap);
+    v.cell = reinterpret_cast<int*>(d + 20 * cap);
     v.ready = reinterpret_cast<uint32_t*>(v.cell + cap);
     v.capacity = cap;
     return v;
 }
-inline size_t vault_bytes(unsigned long long cap) { return kVaultHeaderBytes + (size_t)cap * (19 * 8 + 4 + 4); }
+inline size_t vault_bytes(unsigned long long cap) { return kVaultHeaderBytes + (size_t)cap * (20 * 8 + 4 + 4); }
+constexpr uint32_t kArrivalBit = 0x80000000u;
+__host__ __device__ inline unsigned long long deposit_salt(uint32_t vault_epoch) { return ((unsigned long long)vault_epoch + 1ull) * 0x9E3779B97F4A7C15ull; }
 
 struct TrackArgs
 {

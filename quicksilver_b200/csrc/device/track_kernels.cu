@@ -294,6 +294,44 @@ __device__ __forceinline__ void store_particle(const VaultView& v, unsigned long
     __stcg(v.dirz + i, with_direction ? p.gamma : nan);
 }
 
+// A deposit into a PEER's vault (NVLink stores, no ordering between them and no fence): the record carries the XOR of
+// its own words and a per-launch salt in `check`, so the receiver can tell a complete record from one whose stores are
+// still landing (or from the slot's previous contents) without the sender ever waiting for its stores to be acknowledged.
+__device__ __forceinline__ unsigned long long bits(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ void store_deposit(const VaultView& v, unsigned long long i, const Particle& p, int cell, uint32_t vault_epoch)
+{
+    const double vx = QSB_VX(p), vy = QSB_VY(p), vz = QSB_VZ(p);
+    const unsigned long long t0 = (unsigned long long)(unsigned)p.last_event | ((unsigned long long)(unsigned)p.num_collisions << 32);
+    const unsigned long long t1 = (unsigned long long)(unsigned)p.breed | ((unsigned long long)(unsigned)p.species << 32);
+    unsigned long long x = deposit_salt(vault_epoch) ^ (unsigned long long)(unsigned)cell ^ t0 ^ t1 ^ p.seed ^ p.id;
+    x ^= bits(p.x) ^ bits(p.y) ^ bits(p.z) ^ bits(vx) ^ bits(vy) ^ bits(vz) ^ bits(p.energy) ^ bits(p.weight) ^ bits(p.ttc);
+    x ^= bits(p.age) ^ bits(p.nmfp) ^ bits(p.nseg) ^ bits(p.alpha) ^ bits(p.beta) ^ bits(p.gamma);
+    __stcg(v.x + i, p.x); __stcg(v.y + i, p.y); __stcg(v.z + i, p.z);
+    __stcg(v.vx + i, vx); __stcg(v.vy + i, vy); __stcg(v.vz + i, vz);
+    __stcg(v.energy + i, p.energy); __stcg(v.weight + i, p.weight); __stcg(v.ttc + i, p.ttc);
+    __stcg(v.age + i, p.age); __stcg(v.nmfp + i, p.nmfp); __stcg(v.nseg + i, p.nseg);
+    __stcg(v.seed + i, (unsigned long long)p.seed); __stcg(v.id + i, (unsigned long long)p.id);
+    __stcg(v.cell + i, cell);
+    __stcg(v.tags + i, make_int4(p.last_event, p.num_collisions, p.breed, p.species));
+    __stcg(v.dirx + i, p.alpha); __stcg(v.diry + i, p.beta); __stcg(v.dirz + i, p.gamma);
+    __stcg(v.check + i, x);
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(v.ready + i), "r"(vault_epoch | kArrivalBit) : "memory");
+}
+
+// the receiving side: true when the record in slot i is complete
+__device__ __forceinline__ bool deposit_complete(const VaultView& v, unsigned long long i, uint32_t vault_epoch)
+{
+    unsigned long long x = deposit_salt(vault_epoch) ^ (unsigned long long)(unsigned)__ldcg(v.cell + i);
+    const int4 t = __ldcg(v.tags + i);
+    x ^= (unsigned long long)(unsigned)t.x | ((unsigned long long)(unsigned)t.y << 32);
+    x ^= (unsigned long long)(unsigned)t.z | ((unsigned long long)(unsigned)t.w << 32);
+    x ^= __ldcg(v.seed + i) ^ __ldcg(v.id + i);
+    const double* f64[15] = { v.x, v.y, v.z, v.vx, v.vy, v.vz, v.energy, v.weight, v.ttc, v.age, v.nmfp, v.nseg, v.dirx, v.diry, v.dirz };
+#pragma unroll
+    for (int k = 0; k < 15; ++k) x ^= bits(__ldcg(f64[k] + i));
+    return x == __ldcg(v.check + i);
+}
+
 // ---- nearest facet, full path --------------------------------------------------------------------------
 
 // ray / triangle test of one facet: src/MCT.cc:280-395
@@ -1008,46 +1046,53 @@ __device__ __forceinline__ PeerControl* peer_control(const TrackArgs& a, int ran
 // what a block knows about the peers' current launch (filled once per block at kernel start, see track_kernel)
 struct PeerLaunch { unsigned long long n_in; unsigned int vault_epoch; unsigned int pad; };
 
-// Deposit the particles of all lanes whose history just left this GPU's domain straight into the neighbours' processing
+// Deposit the particles of lanes whose history just left this GPU's domain straight into the neighbours' processing
 // vaults (the reference packs them into per-neighbour MPI buffers and unpacks them on the other side,
-// src/MC_Facet_Crossing_Event.cc:49-67 + src/MC_Particle_Buffer.cc:258-291,452-502).  Runs converged in the service phase,
-// BEFORE the warp retires those histories from the local in-flight count.  Order of the counter updates (what the
-// termination test relies on): own `sent` (performed: its value has come back) -> peer's `inflight` and `tail` (performed)
-// -> peer's `received` -> ... -> own in-flight count drops.  No fence on this path except the release of the slot's
-// ready word (fences with acquire semantics would invalidate this SM's L1 on every crossing).
-__device__ __forceinline__ void send_flush(const TrackArgs& a, const PeerLaunch* launch, const Particle& p, bool pending)
+// src/MC_Facet_Crossing_Event.cc:49-67 + src/MC_Particle_Buffer.cc:258-291,452-502).  Nothing on this path waits for
+// NVLink: a warp that stood still for the round trips of every crossing lost 6 % of a cycle at 2 GPUs and a quarter at 8
+// (measured).  A deposit advances one stage per service phase of its warp: stage 1 issues the remote atomics (slot +
+// counters) and leaves their results in flight; stage 2, a few passes later, reads them (they are back), stores the
+// self-validating record (store_deposit: no fence, no release) and retires the history locally.  The lane keeps the
+// particle in its registers, and takes no new ticket, in between.  Order of the counter updates, which is what the
+// termination test relies on: peer's `sent` and `inflight` raised (performed: stage 2 has consumed their return values)
+// -> own in-flight count drops; peer's `received` raised after its `inflight`.
+struct SendState { int stage; unsigned long long ticket, dep, dep2; };
+
+__device__ __forceinline__ unsigned send_advance(const TrackArgs& a, const PeerLaunch* launch, const Particle& p, SendState& s)
 {
-    if (pending)
+    const DevImage& im = a.im;
+    unsigned retire = 0u;
+    if (s.stage != 0)
     {
-        const DevImage& im = a.im;
         const int face = p.facet >> 2;
         const size_t k = (size_t)p.cell * 6 + face;
         const int rank = __ldg(im.face_nbr_rank + k);
-        atomicAdd(&a.ctl->send_count[rank], 1ull);                                   // statistics only
-        PeerControl* me = peer_control(a, a.my_rank);
         PeerControl* pc = peer_control(a, rank);
-        const unsigned long long sent_before = atomicAdd(&me->sent, 1ull);
-        // the remote atomics are issued only once the local one has returned (address dependency on its value)
-        unsigned long long* remote_inflight = &pc->inflight + (sent_before & 0ull);
-        atomicAdd_system(remote_inflight, 1ull);
-        const unsigned long long ticket = atomicAdd_system(&pc->tail, 1ull);
-        asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&pc->received + (ticket & 0ull)), "l"(1ull) : "memory");
-        const unsigned long long slot = ticket - launch[rank].n_in;
-        if (slot >= a.proc.capacity)
+        if (s.stage == 1)
         {
-            st_release_sys(&pc->overflow, a.peer_epoch);           // the peer's host reports it; the particle is dropped
-            atomicAdd_system(&pc->inflight, 0ull - 1ull);
+            atomicAdd(&a.ctl->send_count[rank], 1ull);                               // statistics only
+            s.dep = atomicAdd_system(&pc->sent, 1ull);              // three results left in flight: nothing here waits for them
+            s.dep2 = atomicAdd_system(&pc->inflight, 1ull);
+            s.ticket = atomicAdd_system(&pc->tail, 1ull);
+            s.stage = 2;
         }
         else
         {
-            const VaultView v = vault_view(a.peer_base[rank], a.proc.capacity);
-            Particle q = p;
-            q.cell = __ldg(im.face_adj_cell + k);                   // the neighbour's flat cell index (one domain per rank)
-            store_particle(v, slot, q, true);
-            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(v.ready + slot), "r"(launch[rank].vault_epoch) : "memory");
+            asm volatile("" :: "l"(s.dep), "l"(s.dep2) : "memory"); // the counter atomics have been performed: their values are here
+            const unsigned long long slot = s.ticket - launch[rank].n_in;
+            retire = 1u;
+            if (slot >= a.proc.capacity)
+            {
+                st_release_sys(&pc->overflow, a.peer_epoch);       // the peer's host reports it; the particle is dropped
+                atomicAdd_system(&pc->inflight, 0ull - 1ull);
+            }
+            else
+                store_deposit(vault_view(a.peer_base[rank], a.proc.capacity), slot, p, __ldg(im.face_adj_cell + k), launch[rank].vault_epoch);
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&pc->received), "l"(1ull) : "memory");
+            s.stage = 0;
         }
     }
-    __syncwarp();
+    return __popc(__ballot_sync(kFullMask, retire != 0u));
 }
 
 // One wave of the termination test (Mattern's four-counter method): lane r reads rank r's control block through NVLink --
@@ -1079,7 +1124,8 @@ __device__ __forceinline__ bool peer_wave(const TrackArgs& a, unsigned lane, uns
 
 // The service warp of a GPU in peer mode (warp 0 of block 0; it tracks nothing) decides global termination.  A rank is
 // passive when its in-flight count is zero; a passive rank becomes active only by a deposit, and a deposit is counted in
-// the sender's `sent` before, and in the receiver's `received` after, it has raised the receiver's in-flight count.  When
+// the receiver's `sent` word while the sender still counts the history as its own, and in the receiver's `received` after
+// it has raised the receiver's in-flight count.  When
 // this GPU is passive the warp takes two waves over all ranks; if every rank was passive in both and the totals satisfy
 // received(wave 1) == sent(wave 1) == received(wave 2) == sent(wave 2), no deposit was under way and no rank was active
 // at the end of the first wave, and termination is stable.  `done` then releases the idle tracking warps.  A launch that
@@ -1089,11 +1135,13 @@ __device__ __noinline__ void peer_service_loop(const TrackArgs& a, unsigned lane
     PeerControl* me = peer_control(a, a.my_rank);
     const unsigned long long t_start = global_timer_ns();
     unsigned sleep = 500;
+    bool seen_idle = false;
     for (;;)
     {
         unsigned long long inflight = 1;
         if (lane == 0) inflight = ld_relaxed_sys(&me->inflight);
         inflight = __shfl_sync(kFullMask, inflight, 0);
+        if (inflight == 0ull && !seen_idle) { seen_idle = true; if (lane == 0) me->first_idle_ns = global_timer_ns() - t_start; }
         bool aborted = ld_relaxed_sys(&me->abort) == a.peer_epoch;
         if (!aborted && inflight == 0ull)
         {
@@ -1104,7 +1152,11 @@ __device__ __noinline__ void peer_service_loop(const TrackArgs& a, unsigned lane
             aborted = ab1 || ab2;
             if (passive2 && r2 == r1 && s2 == r1)
             {
-                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&me->done), "r"(a.peer_epoch) : "memory");
+                if (lane == 0)
+                {
+                    me->done_ns = global_timer_ns() - t_start;
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(&me->done), "r"(a.peer_epoch) : "memory");
+                }
                 return;
             }
         }
@@ -1200,7 +1252,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
     bool spare_valid = false;
     int state = kStateIdle;                             // what this lane's particle needs next (kState*)
     unsigned retired = 0;                               // warp-uniform: histories finished since the last service phase
-    bool send_pending = false;                          // peer mode: history left for a neighbour's domain, record still in registers
+    SendState send = { 0, 0ull, 0ull, 0ull };                 // peer mode: history left for a neighbour's domain, record still in registers
+    unsigned long long diag_send_cycles = 0, diag_send_calls = 0;
 
     // peer mode: before anything can be deposited on a peer, that peer's control words for THIS launch must be in place
     // (its host writes them, then the epoch).  Each block waits for every peer once and keeps what senders need.
@@ -1214,6 +1267,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             while (ld_acquire_sys(&pc->epoch) != a.peer_epoch && global_timer_ns() - t0 < a.watchdog_ns) __nanosleep(500);
             s_launch[threadIdx.x].n_in = ld_relaxed_sys(&pc->n_in);
             s_launch[threadIdx.x].vault_epoch = ld_relaxed_sys(&pc->vault_epoch);
+            if (blockIdx.x == 0 && (int)threadIdx.x != a.my_rank) peer_control(a, a.my_rank)->startup_wait_ns = global_timer_ns() - t0;
         }
         __syncthreads();
         if (blockIdx.x == 0 && threadIdx.x < 32u)
@@ -1237,7 +1291,12 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
         {
             // retire the histories that finished since the last service phase: one reduction per warp.  Secondaries were
             // counted before they became visible, so inflight reaches 0 only when nothing is queued or running.
-            if (__builtin_expect(a.peer_mode != 0, 0) && __any_sync(kFullMask, send_pending)) { send_flush(a, s_launch, p, send_pending); send_pending = false; }
+            if (__builtin_expect(a.peer_mode != 0, 0) && __any_sync(kFullMask, send.stage != 0))
+            {
+                const long long c0 = clock64();
+                retired += send_advance(a, s_launch, p, send);
+                diag_send_cycles += (unsigned long long)(clock64() - c0); diag_send_calls++;
+            }
             if (retired && lane == 0) atomicAdd(a.inflight, 0ull - (unsigned long long)retired);
             retired = 0u;
             census_flush(a, p, census_pending, lane, census_base, census_count, census_leader, census_rank);
@@ -1247,7 +1306,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
             //    time from a batch that was reserved during the PREVIOUS service phase (one atomicAdd whose return value is
             //    only read now, so its latency is off the critical path).  A reserved ticket is an obligation: it is always
             //    handed to a lane eventually.
-            const bool want = state == kStateIdle && ticket == kNoTicket;
+            const bool want = state == kStateIdle && ticket == kNoTicket && send.stage == 0;
             const unsigned want_mask = __ballot_sync(kFullMask, want);
             if (want_mask)
             {
@@ -1293,6 +1352,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                         uint32_t flag;
                         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + slot) : "memory");
                         ready = flag == epoch;
+                        // a peer's deposit: the flag may have overtaken the record, the record vouches for itself
+                        if (__builtin_expect(flag == (epoch | kArrivalBit), 0)) ready = deposit_complete(a.proc, slot, epoch);
                     }
                 }
             }
@@ -1397,7 +1458,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                 else if (outcome == 1)
                 {
                     const int go = facet_crossing_event(a, p, c);
-                    if (go != 1) { state = kStateIdle; finished = true; send_pending = go == 2; }
+                    if (go == 2) { state = kStateIdle; send.stage = 1; }        // retired when the deposit is counted over there
+                    else if (go != 1) { state = kStateIdle; finished = true; }
                 }
                 else { census_pending = true; c.census++; state = kStateIdle; finished = true; }     // stored in the next service phase
             }
@@ -1424,6 +1486,11 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
 
     // flush the per-thread balance counters: warp sum, one atomic per counter per warp
     __syncwarp();
+    if (a.peer_mode && lane == 0 && diag_send_calls)
+    {
+        atomicAdd(&peer_control(a, a.my_rank)->send_cycles, diag_send_cycles);
+        atomicAdd(&peer_control(a, a.my_rank)->send_calls, diag_send_calls);
+    }
     const unsigned int s_seg = warp_sum(c.segments), s_col = warp_sum(c.collisions);
     const unsigned int s_abs = warp_sum(c.absorbs), s_fis = warp_sum(c.fissions), s_pro = warp_sum(c.produced);
     const unsigned int s_esc = warp_sum(c.escapes), s_cen = warp_sum(c.census);

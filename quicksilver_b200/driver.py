@@ -104,6 +104,10 @@ def connect_peers(ctx, dist, rank, world, torch_device, watchdog_seconds=0.0):
     handles = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
     try:
         ctx.peer_connect(handles, watchdog_seconds)
+        import os
+        if os.environ.get("QSB_DEBUG_PEER_MAP_ONLY"):
+            ctx.peer_mode = False
+            return False
     except Exception:
         ok = 0
     flag = torch.tensor([ok], dtype=torch.int32, device=dev)
@@ -267,7 +271,8 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
             dist.barrier()
             torch.cuda.synchronize()
 
-    kernel_s = e2e_s = 0.0
+    kernel_s = e2e_s = device_s = host_s = 0.0
+    sent_total = 0
     segments = 0
     h2d = d2h = 0
     launches0 = 0
@@ -292,10 +297,15 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
         barrier()
         ta = time.perf_counter()
         sim.backend.device_ms = 0.0
-        exchange_rounds(sim.backend, dist, rank, world)
+        _, n_sent = exchange_rounds(sim.backend, dist, rank, world)
         torch.cuda.synchronize()
         tb = time.perf_counter()
+        if timed:
+            sent_total += n_sent
         step_kernel_s = sim.backend.device_ms * 1e-3 if world == 1 else tb - ta
+        if timed:
+            device_s += sim.backend.device_ms * 1e-3
+            host_s += tb - ta
         # (b) `e2e`: host buffers in, host buffers out -- the drop-in call (one GPU) / its two halves around the exchange
         #     rounds (several GPUs), wall clock, copies of the vaults included (streamed under the tracking)
         barrier()
@@ -346,6 +356,9 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
            "segments_rank0": segments / world, "kernel_seconds_rank0": kernel_s, "config": config, "clocks": clocks,
            "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
            "gpu_launches": launches, "traffic": None,
+           "tracking_ms_per_step_rank0": {"boundary_particles_sent": sent_total // max(args.steps, 1),
+                                          "cuda_events_on_kernel_stream": 1e3 * device_s / max(args.steps, 1),
+                                          "host_clock_around_call": 1e3 * host_s / max(args.steps, 1)},
            "balance_check": {"gains": gains, "losses": losses, "conserved": gains == losses, "last_row": rows[-1]}}
     sim.close()
     if world > 1:
