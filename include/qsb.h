@@ -129,8 +129,8 @@ typedef struct qsb_image {
  * ==================================================================================================== */
 typedef struct qsb_mc qsb_mc;
 
-/* sum-reduction over ranks used by cycleInit/cycleFinalize, the stand-in for mpiAllreduce
- * (src/utilsMpi.hh:24-50).  dtype: 0 = f64, 1 = u64.  In place.  NULL (default) = single rank. */
+/* reduction over ranks used by cycleInit/cycleFinalize and the benchmark report, the stand-in for mpiAllreduce
+ * (src/utilsMpi.hh:24-50).  dtype: 0 = f64 sum, 1 = u64 sum, 2 = f64 max.  In place.  NULL (default) = single rank. */
 typedef void (*qsb_allreduce_fn)(void* user, void* buf, int32_t count, int32_t dtype);
 
 /* Parse argv exactly like the reference's getParameters (CLI first, deck overrides: src/Parameters.cc:80-95)
@@ -160,6 +160,15 @@ int  qsb_mc_set_tracking_result(qsb_mc* mc, const qsb_base_particle* census, uin
 int  qsb_mc_cycle_finalize(qsb_mc* mc, uint64_t row[QSB_BAL_COUNT], double* flux);
 int  qsb_mc_cumulative_balance(qsb_mc* mc, uint64_t out[QSB_BAL_COUNT]);
 /* one line of the reference's cycle table (src/Tallies.cc:123-144, src/Tallies.hh:60-76). */
+/* coralBenchmarkCorrectness (src/CoralBenchmark.cc:17-226): the reference's end-of-run self checks for the CORAL decks --
+ * reaction ratios, collisions vs facet crossings, lost particles (all from the cumulative balance) and fluence homogeneity
+ * over this rank's cells (max over ranks through the allreduce hook) -- printed with the reference's own wording.  Empty
+ * when the deck does not set coralBenchmark.  Every rank calls it (the fluence test reduces); rank 0's text is the report.
+ * *passed (optional): number of tests that passed, out of 4. */
+int  qsb_mc_coral_benchmark_report(qsb_mc* mc, const double* fluence, uint64_t n_cells, char* buf, uint64_t cap, uint64_t* needed,
+                                   int32_t* passed);
+/* the reference's closing line: Figure Of Merit = segments / cycle-tracking seconds (src/MC_Fast_Timer.cc:97-104) */
+int  qsb_mc_format_figure_of_merit(qsb_mc* mc, double tracking_seconds, char* buf, uint64_t cap);
 int  qsb_mc_format_cycle_row(qsb_mc* mc, int cycle, const uint64_t row[QSB_BAL_COUNT], double flux,
                              double t_init, double t_track, double t_final, char* buf, uint64_t cap);
 const char* qsb_mc_last_error(qsb_mc* mc);
@@ -216,6 +225,11 @@ int  qsb_get_census(qsb_ctx* ctx, qsb_base_particle* aos, uint64_t cap, uint64_t
 int  qsb_get_balance(qsb_ctx* ctx, uint64_t out[QSB_BAL_COUNT]);
 int  qsb_get_scalar_flux(qsb_ctx* ctx, double* out /* [n_cells][n_groups] */);
 int  qsb_scalar_flux_sum(qsb_ctx* ctx, double* sum);
+/* Fluence (src/Tallies.cc:100-121, part of Tallies::CycleFinalize for the CORAL benchmark decks): add this cycle's scalar
+ * flux, summed over groups, to the running per-cell fluence -- on the device, before the next qsb_cycle_begin clears the
+ * flux; qsb_get_fluence copies the n_cells running totals to the host. */
+int  qsb_fluence_accumulate(qsb_ctx* ctx);
+int  qsb_get_fluence(qsb_ctx* ctx, double* out /* [n_cells] */);
 /* boundary-particle exchange (src/MC_Facet_Crossing_Event.cc:49-67, src/MC_Particle_Buffer.cc): the
  * tracker packs leavers into per-peer slabs of qsb_base_particle + direction cosine (160 B records);
  * the caller moves slabs between ranks (NCCL send/recv) and feeds arrivals back with qsb_put_arrivals. */

@@ -109,6 +109,8 @@ def _declare(lib):
         "qsb_mc_cumulative_balance": (C.c_int, [vp, u64p]),
         "qsb_mc_format_cycle_row": (C.c_int, [vp, C.c_int, u64p, C.c_double, C.c_double, C.c_double, C.c_double,
                                                C.c_char_p, C.c_uint64]),
+        "qsb_mc_coral_benchmark_report": (C.c_int, [vp, _P(C.c_double), C.c_uint64, C.c_char_p, C.c_uint64, u64p, _P(C.c_int32)]),
+        "qsb_mc_format_figure_of_merit": (C.c_int, [vp, C.c_double, C.c_char_p, C.c_uint64]),
         "qsb_mc_last_error": (C.c_char_p, [vp]),
         "qsb_create": (C.c_int, [C.c_int, _P(Image), C.c_double, _P(Options), _P(vp)]),
         "qsb_destroy": (C.c_int, [vp]),
@@ -124,6 +126,8 @@ def _declare(lib):
         "qsb_get_balance": (C.c_int, [vp, u64p]),
         "qsb_get_scalar_flux": (C.c_int, [vp, _P(C.c_double)]),
         "qsb_scalar_flux_sum": (C.c_int, [vp, _P(C.c_double)]),
+        "qsb_fluence_accumulate": (C.c_int, [vp]),
+        "qsb_get_fluence": (C.c_int, [vp, _P(C.c_double)]),
         "qsb_send_counts": (C.c_int, [vp, u64p]),
         "qsb_send_slab": (C.c_int, [vp, C.c_int, _P(vp), u64p]),
         "qsb_clear_sends": (C.c_int, [vp]),

@@ -185,6 +185,123 @@ int qsb_mc_cumulative_balance(qsb_mc* h, uint64_t out[QSB_BAL_COUNT])
     return guarded(h, [&](MonteCarlo& mc) { std::memcpy(out, mc.tallies.balanceCumulative.v, sizeof(uint64_t) * QSB_BAL_COUNT); return QSB_OK; });
 }
 
+// src/CoralBenchmark.cc:17-226, statement by statement; the text is the reference's.
+int qsb_mc_coral_benchmark_report(qsb_mc* h, const double* fluence, uint64_t n_cells, char* buf, uint64_t cap, uint64_t* needed,
+                                  int32_t* passed)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        std::string out;
+        int n_pass = 0;
+        char tmp[512];
+        const int which = mc.params.simulationParams.coralBenchmark;
+        if (which)
+        {
+            const Balance& b = mc.tallies.balanceCumulative;
+            const bool report = mc.rank == 0;
+            {   // BalanceRatioTest (:46-115)
+                const uint64_t absorb = b[QSB_BAL_ABSORB], fission = b[QSB_BAL_FISSION], scatter = b[QSB_BAL_SCATTER];
+                double absorbRatio = 0.04, fissionRatio = 0.05, scatterRatio = 1, percent_tolerance = 1.0;
+                if (which == 2) { fissionRatio = 0.075; scatterRatio = 0.830; absorbRatio = 0.094; percent_tolerance = 1.1; }
+                const double tolerance = percent_tolerance / 100.0;
+                const double a2s = std::abs((absorb / absorbRatio) * (scatterRatio / scatter) - 1);
+                const double a2f = std::abs((absorb / absorbRatio) * (fissionRatio / fission) - 1);
+                const double s2a = std::abs((scatter / scatterRatio) * (absorbRatio / absorb) - 1);
+                const double s2f = std::abs((scatter / scatterRatio) * (fissionRatio / fission) - 1);
+                const double f2a = std::abs((fission / fissionRatio) * (absorbRatio / absorb) - 1);
+                const double f2s = std::abs((fission / fissionRatio) * (scatterRatio / scatter) - 1);
+                const bool pass = !(a2s > tolerance || a2f > tolerance || s2a > tolerance || s2f > tolerance || f2a > tolerance || f2s > tolerance);
+                out += "\nTesting Ratios for Absorbtion, Fission, and Scattering are maintained\n";
+                if (pass)
+                {
+                    std::snprintf(tmp, sizeof tmp, "PASS:: Absorption / Fission / Scatter Ratios maintained with %g%% tolerance\n", tolerance * 100.0);
+                    out += tmp;
+                }
+                else
+                {
+                    std::snprintf(tmp, sizeof tmp, "FAIL:: Absorption / Fission / Scatter Ratios NOT maintained with %g%% tolerance\n", tolerance * 100.0);
+                    out += tmp;
+                    std::snprintf(tmp, sizeof tmp, "absorb:  %12llu\t%g\nscatter: %12llu\t%g\nfission: %12llu\t%g\n", (unsigned long long)absorb, absorbRatio,
+                                  (unsigned long long)scatter, scatterRatio, (unsigned long long)fission, fissionRatio);
+                    out += tmp;
+                    const char* names[6] = { "Absorb to Scatter: ", "Absorb to Fission: ", "Scatter to Absorb: ", "Scatter to Fission:", "Fission to Absorb: ", "Fission to Scatter:" };
+                    const double vals[6] = { a2s, a2f, s2a, s2f, f2a, f2s };
+                    for (int i = 0; i < 6; ++i) { std::snprintf(tmp, sizeof tmp, "Relative %s %g < %g\n", names[i], vals[i], tolerance); out += tmp; }
+                }
+                n_pass += pass;
+            }
+            {   // BalanceEventTest (:117-147)
+                const uint64_t facetCrossing = b[QSB_BAL_NUM_SEGMENTS] - b[QSB_BAL_CENSUS] - b[QSB_BAL_COLLISION];
+                const double ratio = std::abs((double(facetCrossing) / double(b[QSB_BAL_COLLISION])) - 1);
+                const double tolerance = 1.0;
+                const bool pass = !(ratio > (tolerance / 100.0));
+                out += "\nTesting balance between number of facet crossings and reactions\n";
+                if (pass) std::snprintf(tmp, sizeof tmp, "PASS:: Collision to Facet Crossing Ratio maintained even balanced within %g%% tolerance\n", tolerance);
+                else std::snprintf(tmp, sizeof tmp, " FAIL:: Collision to Facet Crossing Ratio balanced NOT maintained within %g%% tolerance\n"
+                                   "\tFacet Crossing: %llu\tCollision: %llu\tRatio: %g\n", tolerance, (unsigned long long)facetCrossing,
+                                   (unsigned long long)b[QSB_BAL_COLLISION], ratio);
+                out += tmp;
+                n_pass += pass;
+            }
+            {   // MissingParticleTest (:149-171)
+                const uint64_t gains = b[QSB_BAL_START] + b[QSB_BAL_SOURCE] + b[QSB_BAL_PRODUCE] + b[QSB_BAL_SPLIT];
+                const uint64_t losses = b[QSB_BAL_ABSORB] + b[QSB_BAL_CENSUS] + b[QSB_BAL_ESCAPE] + b[QSB_BAL_RR] + b[QSB_BAL_FISSION];
+                out += "\nTest for lost / unaccounted for particles in this simulation\n";
+                out += gains == losses ? "PASS:: No Particles Lost During Run\n" : "FAIL:: Particles Were Lost During Run, test for done should have failed\n";
+                n_pass += gains == losses;
+            }
+            {   // FluenceTest (:174-226): this rank's cells (one Fluence domain per mesh domain), max over ranks
+                out += "\nTest Fluence for homogeneity across cells\n";
+                double max_diff = 0.0;
+                const int nDom = (int)mc.flat.domainCellOffset.size() - 1;
+                for (int d = 0; d < nDom && fluence; ++d)
+                {
+                    const size_t first = (size_t)mc.flat.domainCellOffset[d], last = (size_t)mc.flat.domainCellOffset[d + 1];
+                    if (last > n_cells) break;
+                    double local_sum = 0.0;
+                    for (size_t c = first; c < last; ++c) local_sum += fluence[c];
+                    const double average = local_sum / (double)(int)(last - first);
+                    for (size_t c = first; c < last; ++c)
+                    {
+                        const double v = fluence[c];
+                        const double percent_diff = (((v > average) ? v - average : average - v) / ((v + average) / 2.0)) * 100;
+                        max_diff = (max_diff > percent_diff) ? max_diff : percent_diff;
+                    }
+                }
+                if (mc.allreduce && mc.nRanks > 1) mc.allreduce(mc.allreduceUser, &max_diff, 1, 2);
+                const double percent_tolerance = 6.0;
+                if (max_diff > percent_tolerance)
+                {
+                    std::snprintf(tmp, sizeof tmp, "FAIL:: Fluence not homogenous across cells within %g%% tolerance\n"
+                                  "\tTry running more particles or more cycles to see if Max Percent Difference goes down.\n"
+                                  "\tCurrent Max Percent Diff: %4.1f%%\n", percent_tolerance, max_diff);
+                }
+                else
+                {
+                    std::snprintf(tmp, sizeof tmp, "PASS:: Fluence is homogenous across cells with %g%% tolerance\n", percent_tolerance);
+                    n_pass += 1;
+                }
+                out += tmp;
+            }
+            if (!report) out.clear();
+        }
+        if (passed) *passed = n_pass;
+        if (needed) *needed = out.size() + 1;
+        if (buf && cap) std::snprintf(buf, cap, "%s", out.c_str());
+        return QSB_OK;
+    });
+}
+
+int qsb_mc_format_figure_of_merit(qsb_mc* h, double tracking_seconds, char* buf, uint64_t cap)
+{
+    if (!buf || !cap) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        const double segs = (double)mc.tallies.balanceCumulative[QSB_BAL_NUM_SEGMENTS];
+        std::snprintf(buf, cap, "%-25s %12.3e %-25s\n", "Figure Of Merit", tracking_seconds > 0 ? segs / tracking_seconds : 0.0,
+                      "[Num Segments / Cycle Tracking Time]");
+        return QSB_OK;
+    });
+}
+
 // Same columns and widths as the reference's per-cycle line (src/Tallies.hh:60-76, src/Tallies.cc:123-144).
 int qsb_mc_format_cycle_row(qsb_mc* h, int cycle, const uint64_t row[QSB_BAL_COUNT], double flux,
                             double t_init, double t_track, double t_final, char* buf, uint64_t cap)
@@ -266,6 +383,9 @@ extern "C" int qsb_mc_tracking_end(qsb_mc* h, qsb_ctx* ctx)
         double flux = 0.0;
         if ((rc = qsb_get_balance(ctx, bal)) != QSB_OK) return fail(rc);
         if ((rc = qsb_scalar_flux_sum(ctx, &flux)) != QSB_OK) return fail(rc);
+        // Tallies::CycleFinalize adds the cycle's flux to the fluence for the CORAL decks (src/Tallies.cc:90-91); the flux
+        // lives on the device and is cleared by the next qsb_cycle_begin, so that part of the finalize step runs here
+        if (mc.params.simulationParams.coralBenchmark && (rc = qsb_fluence_accumulate(ctx)) != QSB_OK) return fail(rc);
         static const int tracked[] = { QSB_BAL_ABSORB, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_FISSION,
                                        QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
         for (int i : tracked) mc.tallies.balanceTask[i] += bal[i];

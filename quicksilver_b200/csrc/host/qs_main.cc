@@ -62,10 +62,17 @@ int main(int argc, char** argv)
         std::printf("%s", line);
         t_track_total += t2 - t1;
     }
-    uint64_t cum[QSB_BAL_COUNT];
-    qsb_mc_cumulative_balance(mc, cum);
-    // src/MC_Fast_Timer.cc:97-104
-    std::printf("%-25s %12.3e %-25s\n", "Figure Of Merit", cum[QSB_BAL_NUM_SEGMENTS] / t_track_total, "[Num Segments / Cycle Tracking Time]");
+    // coralBenchmarkCorrectness (src/main.cc:73, src/CoralBenchmark.cc) + figure of merit (src/MC_Fast_Timer.cc:97-104)
+    {
+        std::vector<double> fluence((size_t)image.n_cells, 0.0);
+        qsb_get_fluence(ctx, fluence.data());
+        std::vector<char> report(8192);
+        qsb_mc_coral_benchmark_report(mc, fluence.data(), fluence.size(), report.data(), report.size(), nullptr, nullptr);
+        std::printf("%s", report.data());
+        char fom[256];
+        qsb_mc_format_figure_of_merit(mc, t_track_total, fom, sizeof fom);
+        std::printf("%s", fom);
+    }
     qsb_destroy(ctx);
     qsb_mc_destroy(mc);
     return 0;

@@ -91,6 +91,14 @@ class DeviceContext:
         self._check(self._lib.qsb_scalar_flux_sum(self._h, C.byref(s)))
         return s.value
 
+    def fluence_accumulate(self):
+        self._check(self._lib.qsb_fluence_accumulate(self._h))
+
+    def get_fluence(self):
+        out = np.zeros(self.image.n_cells)
+        self._check(self._lib.qsb_get_fluence(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def send_counts(self):
         out = np.zeros(self.n_ranks, dtype=np.uint64)
         self._check(self._lib.qsb_send_counts(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))

@@ -170,6 +170,38 @@ def exchange_rounds(backend, dist, rank, world, max_rounds=100000):
             raise RuntimeError("particle exchange did not terminate")
 
 
+def bind_to_gpu_numa_node(device):
+    """Run this process (and therefore first-touch its page-locked vaults) on the CPUs of the NUMA node the GPU hangs off, so
+    that the streamed host vaults do not cross the socket interconnect on their way to and from the device.  Several ranks
+    of one node otherwise land wherever the scheduler puts them.  Best effort: returns the node, or None if anything about
+    the topology cannot be read (no sysfs, no nvidia-smi, a single node)."""
+    import os
+    import subprocess
+    if os.environ.get("QSB_NO_NUMA_BIND"):
+        return None
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip().splitlines()[0].strip()
+        dom, rest = out.split(":", 1)                      # "00000000:1B:00.0" -> "0000:1b:00.0"
+        bdf = ("%04x:%s" % (int(dom, 16), rest)).lower()
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 class Simulation:
     """One rank of a run: host model + device context + the cycle loop."""
 
@@ -179,6 +211,7 @@ class Simulation:
         protocol pass a CPU stand-in so that the N-rank logic runs under gloo on a machine without GPUs."""
         self.rank, self.world, self.dist = rank, world, dist
         self.torch_device = "cuda:%d" % device
+        self.numa_node = bind_to_gpu_numa_node(device) if (make_backend is None and world > 1) else None
         self.mc = host_mod.MonteCarlo(argv, rank, world, allreduce=self._allreduce if world > 1 else None)
         self.ctx = None
         if make_backend is not None:
@@ -199,15 +232,21 @@ class Simulation:
             if connect_peers(self.ctx, dist, rank, world, self.torch_device, float(os.environ.get("QSB_PEER_WATCHDOG_S", "0"))):
                 self.exchange = "peer"
 
-    def _allreduce(self, arr):
+    def _allreduce(self, arr, op="sum"):
         import torch
         is_cuda = self.dist.get_backend() == "nccl"
         view = arr.view(np.int64) if arr.dtype == np.uint64 else arr
         t = torch.from_numpy(view.copy())
         if is_cuda:
             t = t.to(self.torch_device)
-        self.dist.all_reduce(t)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         view[:] = t.cpu().numpy()
+
+    def report(self, tracking_seconds):
+        """the reference's closing report (src/main.cc:66-80): CORAL self checks + figure of merit; text on rank 0."""
+        fluence = self.ctx.get_fluence() if self.ctx is not None else None
+        text, passed = self.mc.coral_benchmark_report(fluence)
+        return text + (self.mc.format_figure_of_merit(tracking_seconds) if self.rank == 0 else ""), passed
 
     def cycle(self):
         """one cycle; returns (global balance row, global flux sum, timings dict)."""
@@ -351,7 +390,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
               "kernels": "fast" if args.fast else "validation", "timing": "inputs larger than L2 (vault %.0f MB, mesh %.0f MB per GPU); value: %s; e2e: wall clock around the "
               "drop-in call with host vaults" % (w["particles"] * 160 / 1e6, n ** 3 * 1.2e-3,
               "CUDA events on the tracking stream" if world == 1 else "host clock between device syncs + barriers around the exchange rounds, max over ranks"),
-              "scale": args.scale, "exchange": getattr(sim, "exchange", "none") if world > 1 else "none"}
+              "scale": args.scale, "exchange": getattr(sim, "exchange", "none") if world > 1 else "none", "numa_node_rank0": sim.numa_node}
     out = {"segments_total": segments, "kernel_seconds_max": kernel_max, "e2e_seconds_max": e2e_max,
            "segments_rank0": segments / world, "kernel_seconds_rank0": kernel_s, "config": config, "clocks": clocks,
            "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),

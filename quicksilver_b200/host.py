@@ -44,10 +44,15 @@ class MonteCarlo:
             pass
 
     def set_allreduce(self, fn):
-        """fn(numpy array) must sum the array over ranks in place (stand-in for mpiAllreduce)."""
+        """fn(numpy array[, op]) must reduce the array over ranks in place (stand-in for mpiAllreduce); op is "sum"
+        (default) or "max" (the fluence test of the benchmark report)."""
         def trampoline(_user, buf, count, dtype):
-            ct = C.c_double if dtype == 0 else C.c_uint64
-            fn(np.ctypeslib.as_array(C.cast(buf, C.POINTER(ct)), (count,)))
+            ct = C.c_uint64 if dtype == 1 else C.c_double
+            arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(ct)), (count,))
+            if dtype == 2:
+                fn(arr, "max")
+            else:
+                fn(arr)
         self._cb = _capi.ALLREDUCE_FN(trampoline)
         self._check(self._lib.qsb_mc_set_allreduce(self._h, self._cb, None))
 
@@ -123,6 +128,22 @@ class MonteCarlo:
         row = np.zeros(BAL_COUNT, dtype=np.uint64)
         self._check(self._lib.qsb_mc_cumulative_balance(self._h, row.ctypes.data_as(C.POINTER(C.c_uint64))))
         return row
+
+    def coral_benchmark_report(self, fluence=None):
+        """coralBenchmarkCorrectness (src/CoralBenchmark.cc): (report text -- empty unless the deck sets coralBenchmark,
+        and on ranks other than 0 --, number of tests passed out of 4).  fluence: this rank's per-cell fluence."""
+        f = None if fluence is None else np.ascontiguousarray(fluence, dtype=np.float64)
+        ptr = None if f is None else f.ctypes.data_as(C.POINTER(C.c_double))
+        n = 0 if f is None else len(f)
+        need, passed = C.c_uint64(), C.c_int32()
+        buf = C.create_string_buffer(8192)
+        self._check(self._lib.qsb_mc_coral_benchmark_report(self._h, ptr, n, buf, 8192, C.byref(need), C.byref(passed)))
+        return buf.value.decode(), passed.value
+
+    def format_figure_of_merit(self, tracking_seconds):
+        buf = C.create_string_buffer(256)
+        self._check(self._lib.qsb_mc_format_figure_of_merit(self._h, float(tracking_seconds), buf, 256))
+        return buf.value.decode()
 
     def format_cycle_row(self, cycle, row, flux, t_init=0.0, t_track=0.0, t_final=0.0):
         buf = C.create_string_buffer(2048)

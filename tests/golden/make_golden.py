@@ -82,5 +82,34 @@ def main():
                 case, os.path.getsize(path) / 1e3, cycles, len(out["cycle0/tracking_input"]), len(out["cycle0/census"])))
 
 
+# the reference's closing report (coralBenchmarkCorrectness, src/CoralBenchmark.cc) as its binary prints it
+REPORT_CASES = [("Coral2_P1_1", dict(nSteps=10)), ("Coral2_P2_1", dict(nSteps=10)), ("Coral2_P1_1:short", dict(nSteps=2, nParticles=20480))]
+
+
+def coral_reports():
+    import json
+    import helpers as H
+    out = {}
+    for name, over in REPORT_CASES:
+        with tempfile.TemporaryDirectory() as tmp:
+            deck = decks.write_deck(decks.derive(name.split(":")[0], over), os.path.join(tmp, "d.inp"))
+            text = subprocess.run([H.REF_QS, "-i", deck], env=dict(os.environ, OMP_NUM_THREADS="8"), stdout=subprocess.PIPE,
+                                  stderr=subprocess.DEVNULL, text=True, check=True).stdout
+        lines = text.splitlines()
+        first = [k for k, l in enumerate(lines) if l.startswith("Testing Ratios")][0] - 1
+        last = [k for k, l in enumerate(lines) if "Fluence" in l and ("PASS" in l or "FAIL" in l)][0]
+        while last + 1 < len(lines) and lines[last + 1].startswith("\t"):
+            last += 1
+        out[name] = {"overrides": over, "report": "\n".join(lines[first:last + 1]) + "\n"}
+    with open(os.path.join(HERE, "coral_reports.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("coral_reports.json: %d reports" % len(out))
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["reports"]:
+        coral_reports()
+    else:
+        main()
+        if not sys.argv[1:]:
+            coral_reports()

@@ -176,3 +176,23 @@ def test_drop_in_streams_whole_census_chunks(tmp_path, monkeypatch):
         # the next cycle must start from identical vaults: carry the oracle's census order into the GPU twin as well
         gpu.set_tracking_result(want.census, np.zeros(13, np.uint64), 0.0)
     ctx.close()
+
+
+def test_device_fluence_accumulates_the_cycle_flux(tmp_path):
+    """qsb_fluence_accumulate (Fluence::compute, src/Tallies.cc:100-121, done on the device by the drop-in call for the CORAL
+    decks) against the per-cell sums of the scalar flux the device itself reports, cycle after cycle; then the reference's
+    report text from the host model with that fluence."""
+    deck = decks.write_deck(decks.derive("Coral2_P1_1", nx=8, ny=8, nz=8, lx=8, ly=8, lz=8, nParticles=20480, nSteps=3), str(tmp_path / "p1.inp"))
+    mc = host.MonteCarlo(["-i", deck])
+    ctx = device.DeviceContext(mc.image, mc.get_double("dt"), validation=True, particle_capacity=1 << 20)
+    want = np.zeros(mc.image.n_cells)
+    for _ in range(3):
+        mc.cycle_init()
+        mc.cycle_tracking(ctx)                       # coralBenchmark deck: accumulates the fluence on the device
+        want += ctx.get_scalar_flux().sum(axis=1)
+        mc.cycle_finalize()
+    got = ctx.get_fluence()
+    assert np.allclose(got, want, rtol=1e-12, atol=0.0)
+    text, passed = mc.coral_benchmark_report(got)
+    assert text.count("PASS::") == passed and "Test Fluence for homogeneity across cells" in text
+    ctx.close()
