@@ -1228,7 +1228,10 @@ __device__ __forceinline__ void census_flush(const TrackArgs& a, const Particle&
 __device__ __forceinline__ unsigned int warp_sum(unsigned int v) { return __reduce_add_sync(kFullMask, v); }
 
 // ---- the persistent history kernel ---------------------------------------------------------------------
-template <int kDummy>
+// kPeer = 1: the instance launched when the peer exchange is connected.  The single-GPU instance carries none of that
+// code: the hot loop is instruction-fetch sensitive (the warp-state samples show it), and the deposit / termination paths
+// inlined into the service phase cost 4 % of the single-GPU rate when they were merely present.
+template <int kDummy, int kPeer>
 #ifndef QSB_MIN_BLOCKS
 #define QSB_MIN_BLOCKS 3
 #endif
@@ -1257,8 +1260,8 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
 
     // peer mode: before anything can be deposited on a peer, that peer's control words for THIS launch must be in place
     // (its host writes them, then the epoch).  Each block waits for every peer once and keeps what senders need.
-    __shared__ PeerLaunch s_launch[kMaxPeers];
-    if (a.peer_mode)
+    __shared__ PeerLaunch s_launch[kPeer ? kMaxPeers : 1];
+    if (kPeer && a.peer_mode)
     {
         if ((int)threadIdx.x < a.im.n_ranks)
         {
@@ -1291,7 +1294,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
         {
             // retire the histories that finished since the last service phase: one reduction per warp.  Secondaries were
             // counted before they became visible, so inflight reaches 0 only when nothing is queued or running.
-            if (__builtin_expect(a.peer_mode != 0, 0) && __any_sync(kFullMask, send.stage != 0))
+            if (kPeer && a.peer_mode && __any_sync(kFullMask, send.stage != 0))
             {
                 const long long c0 = clock64();
                 retired += send_advance(a, s_launch, p, send);
@@ -1370,7 +1373,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
                 unsigned long long inflight = 1;
                 if (lane == 0)
                 {
-                    if (!a.peer_mode) inflight = *((volatile unsigned long long*)a.inflight);
+                    if (!(kPeer && a.peer_mode)) inflight = *((volatile unsigned long long*)a.inflight);
                     else
                     {
                         const PeerControl* me = peer_control(a, a.my_rank);
@@ -1486,7 +1489,7 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
 
     // flush the per-thread balance counters: warp sum, one atomic per counter per warp
     __syncwarp();
-    if (a.peer_mode && lane == 0 && diag_send_calls)
+    if (kPeer && a.peer_mode && lane == 0 && diag_send_calls)
     {
         atomicAdd(&peer_control(a, a.my_rank)->send_cycles, diag_send_cycles);
         atomicAdd(&peer_control(a, a.my_rank)->send_calls, diag_send_calls);
@@ -1529,15 +1532,22 @@ __global__ void __launch_bounds__(128, QSB_MIN_BLOCKS) track_kernel(const __grid
 
 void QSB_LAUNCH_NAME(const TrackArgs& a, int grid, int block, cudaStream_t s)
 {
-    track_kernel<QSB_VALIDATION><<<grid, block, 0, s>>>(a);
+    if (a.peer_mode) track_kernel<QSB_VALIDATION, 1><<<grid, block, 0, s>>>(a);
+    else             track_kernel<QSB_VALIDATION, 0><<<grid, block, 0, s>>>(a);
 }
 
 void QSB_ATTR_NAME(int* regs, int* max_blocks_per_sm, int block)
 {
     cudaFuncAttributes attr;
-    if (cudaFuncGetAttributes(&attr, track_kernel<QSB_VALIDATION>) == cudaSuccess && regs) *regs = attr.numRegs;
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, track_kernel<QSB_VALIDATION>, block, 0);
+    // both instances must be fully resident (the kernel is persistent): report the tighter of the two
+    int r = 0, nb = 1 << 30;
+    if (cudaFuncGetAttributes(&attr, track_kernel<QSB_VALIDATION, 0>) == cudaSuccess) r = attr.numRegs;
+    if (cudaFuncGetAttributes(&attr, track_kernel<QSB_VALIDATION, 1>) == cudaSuccess && attr.numRegs > r) r = attr.numRegs;
+    if (regs) *regs = r;
+    int n0 = 0, n1 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, track_kernel<QSB_VALIDATION, 0>, block, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, track_kernel<QSB_VALIDATION, 1>, block, 0);
+    nb = n0 < n1 ? n0 : n1;
     if (max_blocks_per_sm) *max_blocks_per_sm = nb;
 }
 
