@@ -6,6 +6,7 @@
 #include <stdexcept>
 
 #include "../qs_rng.h"
+#include "../qs_cycle_init.h"
 
 #include <cuda_runtime_api.h>
 #include <cstdlib>
@@ -60,6 +61,14 @@ MonteCarlo::MonteCarlo(const Parameters& p, int rank_, int nRanks_)
     if (nRanks < 1 || rank < 0 || rank >= nRanks) throw std::runtime_error("bad rank / n_ranks");
     if (p.simulationParams.nParticles / (uint64_t)nRanks == 0)
         throw std::runtime_error("not enough particles for each rank");
+    // the closed form of the facet -> points table used by the shared cycle-init code must be the mesh builder's table
+    for (int f = 0; f < 24; ++f)
+    {
+        int p0, p1, p2;
+        qs_facet_points(f, &p0, &p1, &p2);
+        if (p0 != kFacetPoints[f][0] || p1 != kFacetPoints[f][1] || p2 != kFacetPoints[f][2])
+            throw std::runtime_error("internal: qs_facet_points disagrees with the facet table");
+    }
     initNuclearData(params, nuclearData, materialDatabase);
     initMesh(params, materialDatabase, rank, nRanks, ddc, domain);
     buildImage();
@@ -191,61 +200,48 @@ void cycleInit(MonteCarlo& mc)
 
 namespace {
 
-// 6 x signed volume of the tet (p0,p1,p2,apex)  (src/MCT.cc:627-646)
-double tetDet(const double* a, const double* b, const double* c, const Vec3& apex)
+template <class M>
+void sourceCells(MonteCarlo& mc, double weight)
 {
-    const double v0x = a[0] - apex.x, v0y = a[1] - apex.y, v0z = a[2] - apex.z;
-    const double v1x = b[0] - apex.x, v1y = b[1] - apex.y, v1z = b[2] - apex.z;
-    const double v2x = c[0] - apex.x, v2y = c[1] - apex.y, v2z = c[2] - apex.z;
-    return v0z * (v1x * v2y - v1y * v2x) + v0y * (v1z * v2x - v1x * v2z) + v0x * (v1y * v2z - v1z * v2y);
-}
-
-// uniform point in the cell: pick one of the 24 centre-apex tets by volume, then fold the unit cube
-// into the tet's barycentric simplex (src/MCT.cc:143-226)
-void generateCoordinate(uint64_t* seed, const double* nodes, double cellVolume, double out[3])
-{
-    const Vec3 center = cellPosition(nodes);
-    const double whichVolume = qs_rng_sample(seed) * 6.0 * cellVolume;
-    double running = 0.0;
-    int facet = -1;
-    const double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
-    while (running < whichVolume)
+    const SimulationParameters& sp = mc.params.simulationParams;
+    const double dt = mc.timeStep;
+    for (size_t di = 0; di < mc.domain.size(); ++di)
     {
-        ++facet;
-        if (facet == 24) break;
-        p0 = nodes + 3 * kFacetPoints[facet][0];
-        p1 = nodes + 3 * kFacetPoints[facet][1];
-        p2 = nodes + 3 * kFacetPoints[facet][2];
-        running += tetDet(p0, p1, p2, center);
+        Domain& d = mc.domain[di];
+        for (int c = 0; c < d.nCells; ++c)
+        {
+            const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
+            const int n = (int)(cellWeight / weight);
+            for (int i = 0; i < n; ++i)
+            {
+                qs_source_particle sp1;
+                qs_source_one<M>(d.sourceTally[c]++ + d.cellId[c], &d.nodes[(size_t)c * 42], d.volume[c], sp.eMin, sp.eMax, dt, &sp1);
+                qsb_base_particle p;
+                std::memset(&p, 0, sizeof(p));
+                p.random_number_seed = sp1.random_number_seed;
+                p.identifier = sp1.identifier;
+                for (int k = 0; k < 3; ++k) { p.coordinate[k] = sp1.coordinate[k]; p.velocity[k] = sp1.velocity[k]; }
+                p.kinetic_energy = sp1.kinetic_energy;
+                p.domain = (int32_t)di; p.cell = c;
+                p.weight = weight;
+                p.num_mean_free_paths = sp1.num_mean_free_paths;
+                p.time_to_census = sp1.time_to_census;
+                p.last_event = QSB_EV_CENSUS;        // MC_Particle's default (src/MC_Base_Particle.hh:259)
+                p.species = 0;
+                mc.processing.push_back(p);
+                mc.tallies.balanceTask[QSB_BAL_SOURCE]++;
+            }
+        }
     }
-    double r1 = qs_rng_sample(seed), r2 = qs_rng_sample(seed), r3 = qs_rng_sample(seed);
-    if (r1 + r2 > 1.0) { r1 = 1.0 - r1; r2 = 1.0 - r2; }
-    if (r2 + r3 > 1.0)           { const double t = r3; r3 = 1.0 - r1 - r2; r2 = 1.0 - t; }
-    else if (r1 + r2 + r3 > 1.0) { const double t = r3; r3 = r1 + r2 + r3 - 1.0; r1 = 1.0 - r2 - t; }
-    const double r4 = 1.0 - r1 - r2 - r3;
-    if (!p0) { out[0] = out[1] = out[2] = 0.0; return; }      // r == 0: the reference bails out with the origin
-    out[0] = (r4 * center.x + r1 * p0[0] + r2 * p1[0] + r3 * p2[0]);
-    out[1] = (r4 * center.y + r1 * p0[1] + r2 * p1[1] + r3 * p2[1]);
-    out[2] = (r4 * center.z + r1 * p0[2] + r2 * p1[2] + r3 * p2[2]);
-}
-
-const double kNeutronRestMassEnergy = 9.395656981095e+2;   // MeV   (src/PhysicalConstants.hh:10-12)
-const double kPi = 3.1415926535897932;
-const double kSpeedOfLight = 2.99792458e+10;               // cm/s
-
-double speedFromEnergy(double e)                            // src/MC_SourceNow.cc:169-177
-{
-    return kSpeedOfLight * std::sqrt(e * (e + 2.0 * (kNeutronRestMassEnergy)) /
-                                     ((e + kNeutronRestMassEnergy) * (e + kNeutronRestMassEnergy)));
 }
 
 } // namespace
 
-void sourceNow(MonteCarlo& mc)
+// total source weight of the cycle over ALL ranks (src/MC_SourceNow.cc:41-57) -> weight of one source particle (:59-61)
+double sourceParticleWeight(MonteCarlo& mc)
 {
     const SimulationParameters& sp = mc.params.simulationParams;
     const double dt = mc.timeStep;
-
     double localWeight = 0;
     for (const Domain& d : mc.domain)
         for (int c = 0; c < d.nCells; ++c)
@@ -260,54 +256,14 @@ void sourceNow(MonteCarlo& mc)
     else mc.reduceSum(&totalWeight, 1);
 
     const double sourceFraction = 0.1;
-    const double weight = totalWeight / (sourceFraction * sp.nParticles);
-    mc.sourceParticleWeight = weight;
-
-    for (size_t di = 0; di < mc.domain.size(); ++di)
-    {
-        Domain& d = mc.domain[di];
-        for (int c = 0; c < d.nCells; ++c)
-        {
-            const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
-            const int n = (int)(cellWeight / weight);
-            for (int i = 0; i < n; ++i)
-            {
-                qsb_base_particle p;
-                std::memset(&p, 0, sizeof(p));
-                uint64_t s = d.sourceTally[c]++ + d.cellId[c];
-                p.random_number_seed = qs_rng_spawn(&s);
-                p.identifier = s;
-
-                generateCoordinate(&p.random_number_seed, &d.nodes[(size_t)c * 42], d.volume[c], p.coordinate);
-
-                // isotropic direction (src/DirectionCosine.cc:5-13)
-                const double gamma = 1.0 - 2.0 * qs_rng_sample(&p.random_number_seed);
-                const double sineGamma = std::sqrt((1.0 - (gamma * gamma)));
-                const double phi = kPi * (2.0 * qs_rng_sample(&p.random_number_seed) - 1.0);
-                const double alpha = sineGamma * std::cos(phi);
-                const double beta = sineGamma * std::sin(phi);
-
-                p.kinetic_energy = (sp.eMax - sp.eMin) * qs_rng_sample(&p.random_number_seed) + sp.eMin;
-                const double speed = speedFromEnergy(p.kinetic_energy);
-                p.velocity[0] = speed * alpha; p.velocity[1] = speed * beta; p.velocity[2] = speed * gamma;
-                p.domain = (int32_t)di; p.cell = c;
-                p.weight = weight;
-                p.num_mean_free_paths = -1.0 * std::log(qs_rng_sample(&p.random_number_seed));
-                p.time_to_census = dt * qs_rng_sample(&p.random_number_seed);
-                p.last_event = QSB_EV_CENSUS;        // MC_Particle's default (src/MC_Base_Particle.hh:259)
-                p.species = 0;
-                mc.processing.push_back(p);
-                mc.tallies.balanceTask[QSB_BAL_SOURCE]++;
-            }
-        }
-    }
+    return totalWeight / (sourceFraction * sp.nParticles);
 }
 
-void populationControl(MonteCarlo& mc)
+// split / roulette factor of PopulationControl (src/PopulationControl.cc:20-63) for a rank holding localCount particles
+double populationControlFactor(MonteCarlo& mc, uint64_t localCount)
 {
     const SimulationParameters& sp = mc.params.simulationParams;
     uint64_t target = sp.nParticles;
-    const uint64_t localCount = mc.processing.size();
     uint64_t globalCount = localCount;
     double factor = 1.0;
     if (sp.loadBalance)
@@ -320,6 +276,21 @@ void populationControl(MonteCarlo& mc)
         mc.reduceSum(&globalCount, 1);
         factor = (double)target / (double)globalCount;
     }
+    return factor;
+}
+
+void sourceNow(MonteCarlo& mc)
+{
+    const double weight = sourceParticleWeight(mc);
+    mc.sourceParticleWeight = weight;
+    if (mc.strictMath) sourceCells<QsStrictMath>(mc, weight);
+    else               sourceCells<QsLibmMath>(mc, weight);
+}
+
+void populationControl(MonteCarlo& mc)
+{
+    const uint64_t localCount = mc.processing.size();
+    const double factor = populationControlFactor(mc, localCount);
     if (factor == 1.0) return;
 
     // Every particle decides from its own stream, so the result does not depend on vault order; the
@@ -331,18 +302,14 @@ void populationControl(MonteCarlo& mc)
     for (size_t i = 0; i < localCount; ++i)
     {
         qsb_base_particle p = v[i];                     // by value: push_back below may reallocate
-        const double r = qs_rng_sample(&p.random_number_seed);
+        const int copies = qs_population_control_one(factor, &p.random_number_seed, &p.weight);
         if (factor < 1)
         {
-            if (r > factor) { bal[QSB_BAL_RR]++; continue; }
-            p.weight /= factor;
+            if (copies < 0) { bal[QSB_BAL_RR]++; continue; }
             v[keep++] = p;
         }
         else
         {
-            int copies = (int)std::floor(factor);
-            if (r > (factor - copies)) copies--;
-            p.weight /= factor;
             qsb_base_particle child = p;
             for (int k = 0; k < copies; ++k)
             {
@@ -367,12 +334,8 @@ void rouletteLowWeightParticles(MonteCarlo& mc)
     for (size_t i = 0; i < v.size(); ++i)
     {
         qsb_base_particle& p = v[i];
-        if (p.weight <= weightCutoff)
-        {
-            const double r = qs_rng_sample(&p.random_number_seed);
-            if (r <= cutoff) p.weight /= cutoff;
-            else { mc.tallies.balanceTask[QSB_BAL_RR]++; continue; }
-        }
+        if (!qs_roulette_low_weight_one(cutoff, weightCutoff, &p.random_number_seed, &p.weight))
+        { mc.tallies.balanceTask[QSB_BAL_RR]++; continue; }
         if (keep != i) v[keep] = p;
         ++keep;
     }

@@ -76,6 +76,19 @@ public:
     double            timeStep;
     int               cycle = 0;
     double            sourceParticleWeight = 0.0;
+    // 0: libm log/sin/cos in MC_SourceNow (the reference's bits); 1: the portable functions of qs_strict_math.h, which the
+    // device cycle-init kernel evaluates to the same bits (qsb_mc_set_strict_math)
+    bool              strictMath = false;
+
+    // ---- device-resident cycles (qsb_mc_cycle_init_resident / qsb_mc_cycle_tracking_resident, capi_host.cc) ----
+    // The particle population lives in the device context's vaults from one cycle to the next; the host model keeps the
+    // counts it needs for the balance bookkeeping and the source plan it hands to the device.
+    bool                  residentCensus = false;   // the census of the last cycle is in the device's census vault
+    uint64_t              residentCensusCount = 0;
+    std::vector<int32_t>  sourceOffsets;            // [nCells+1] prefix sum of the per-cell source counts (flat cell order)
+    std::vector<uint64_t> sourceTallyFlat;          // [nCells] scratch: per-cell running source counts handed to the device
+    double                sourcePlanWeight = -1.0;  // source particle weight the plan was built for
+    uint64_t              sourcePlanId = 0;         // bumped whenever the plan or the host-side tallies change under the device
 
     qsb_allreduce_fn  allreduce = nullptr;
     void*             allreduceUser = nullptr;
@@ -101,6 +114,10 @@ public:
 void cycleInit(MonteCarlo& mc);
 // src/MC_SourceNow.cc:28-133
 void sourceNow(MonteCarlo& mc);
+// the two global numbers of cycleInit: weight of one source particle (src/MC_SourceNow.cc:41-61) and the split / roulette
+// factor for a rank holding localCount particles (src/PopulationControl.cc:20-63); both reduce over ranks
+double sourceParticleWeight(MonteCarlo& mc);
+double populationControlFactor(MonteCarlo& mc, uint64_t localCount);
 // src/PopulationControl.cc:20-122, :127-171
 void populationControl(MonteCarlo& mc);
 void rouletteLowWeightParticles(MonteCarlo& mc);
