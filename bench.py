@@ -201,6 +201,7 @@ def main():
                                  "reference's 1.8 KB of geometry per segment (results bit-identical); `traffic` is what the kernel really "
                                  "moves (ncu), ~32 B/segment -- the kernel is latency / issue bound, see DESIGN.md section 5"},
             "tracking_ms_per_step_rank0": result["tracking_ms_per_step_rank0"],
+            "whole_cycle": result.get("whole_cycle"),
             "balance_check": result["balance_check"]}
     if args.cpu_baseline and world == 1:
         try:

@@ -146,6 +146,9 @@ int  qsb_mc_get_double(qsb_mc* mc, const char* key, double* out);     /* dt, lx,
 
 /* cycleInit (src/main.cc:96-121): swap census -> processing, source, population control, roulette. */
 int  qsb_mc_cycle_init(qsb_mc* mc);
+/* 0 (default): MC_SourceNow evaluates log/sin/cos with libm -- the reference binary's bits; 1: with the portable
+ * functions of csrc/qs_strict_math.h, which the device evaluates to the same bits (validation of the device cycleInit). */
+int  qsb_mc_set_strict_math(qsb_mc* mc, int on);
 /* processing vault (tracking input) as one contiguous AoS; valid until the next qsb_mc_* call. */
 int  qsb_mc_processing(qsb_mc* mc, const qsb_base_particle** aos, uint64_t* n);
 /* processed vault (this cycle's census, the next cycle's carried-over particles); n may be NULL. */
@@ -203,6 +206,44 @@ int  qsb_destroy(qsb_ctx* ctx);
 /* clearCrossSectionCache + per-cycle flux/balance reset (src/main.cc:101-103, src/Tallies.cc:75-93);
  * swaps census -> processing on the device when keep_census != 0. */
 int  qsb_cycle_begin(qsb_ctx* ctx, int keep_census);
+/* ---- device-resident cycles: cycleInit on the device (src/main.cc:96-121), the population never leaves HBM -------------
+ * qsb_cycle_init_resident stands for qsb_cycle_begin + qsb_put_particles of a cycle: it clears the cycle's tallies like
+ * qsb_cycle_begin and then fills the processing vault ON THE DEVICE from (i) the census vault of the previous cycle and
+ * (ii) this cycle's source particles (MC_SourceNow, src/MC_SourceNow.cc:28-133), each passed through population control
+ * (src/PopulationControl.cc:20-122) and the low-weight roulette (src/PopulationControl.cc:127-171) -- one kernel, same
+ * per-particle random-number streams and arithmetic as the host model (qsb_mc_cycle_init in strict-math mode gives the
+ * same particles bit for bit).  The caller supplies the numbers that need other ranks: the weight of a source particle, the
+ * per-cell source counts that follow from it, and the split / roulette factor target / global count.  qsb_track follows
+ * as usual; the census stays in the census vault for the next qsb_cycle_init_resident (or qsb_get_census).
+ * Not available while the previous cycle's census was streamed to the host (qsb_stream_begin): that census is not in
+ * the vault.  qsb_put_census seeds the census vault from host records (first resident cycle after host cycles, restart). */
+typedef struct qsb_cycle_init_args {
+    uint64_t        plan_id;            /* the two arrays below are read (and kept on the device) only when this differs
+                                           from the previous call's; the device advances its running counts itself     */
+    const int32_t*  source_offsets;     /* [n_cells+1] prefix sum over flat cells of (int)(cellWeight / source_weight)
+                                           (src/MC_SourceNow.cc:72-76)                                                  */
+    const uint64_t* source_tally;       /* [n_cells] the cells' running source counts before this cycle
+                                           (MC_Cell_State::_sourceTally, src/MC_SourceNow.cc:92)                       */
+    double          source_weight;      /* weight of one source particle (src/MC_SourceNow.cc:59-61)                   */
+    double          e_min, e_max;       /* source energy range (src/MC_SourceNow.cc:108-110)                           */
+    double          split_factor;       /* population-control factor (src/PopulationControl.cc:32-57); 1.0 = none       */
+    double          low_weight_cutoff;  /* deck lowWeightCutoff, relative to source_weight; <= 0 = off                 */
+} qsb_cycle_init_args;
+
+typedef struct qsb_cycle_init_result {
+    uint64_t n_start;                   /* census particles carried over (Balance::_start)                             */
+    uint64_t n_source;                  /* source particles created (Balance::_source)                                 */
+    uint64_t n_rr;                      /* killed by population control + low-weight roulette (Balance::_rr)           */
+    uint64_t n_split;                   /* split copies made (Balance::_split)                                         */
+    uint64_t n_processing;              /* records now in the processing vault                                         */
+    float    device_ms;                 /* CUDA-event time of the kernel                                               */
+    uint32_t n_launches;
+} qsb_cycle_init_result;
+
+int  qsb_cycle_init_resident(qsb_ctx* ctx, const qsb_cycle_init_args* args, qsb_cycle_init_result* result);
+/* host records -> census vault (replaces its contents); the next qsb_cycle_init_resident carries them over. */
+int  qsb_put_census(qsb_ctx* ctx, const qsb_base_particle* aos, uint64_t n);
+
 /* host AoS vault -> device SoA processing vault (append). */
 int  qsb_put_particles(qsb_ctx* ctx, const qsb_base_particle* aos, uint64_t n);
 /* run all local histories to exhaustion, secondaries included (src/main.cc:163-283 for one rank). */
@@ -272,6 +313,24 @@ int  qsb_mc_cycle_tracking(qsb_mc* mc, qsb_ctx* ctx, qsb_track_stats* stats);
  * end = qsb_stream_end + balance + flux sum into the host model's tallies. */
 int  qsb_mc_tracking_begin(qsb_mc* mc, qsb_ctx* ctx);
 int  qsb_mc_tracking_end(qsb_mc* mc, qsb_ctx* ctx);
+
+/* ---- the whole cycle with the population resident on the device ----------------------------------
+ *   qsb_mc_cycle_init_resident      cycleInit (src/main.cc:96-121): the host model supplies the global numbers (source
+ *                                   weight, per-cell source counts, split factor -- reduced over ranks through the
+ *                                   allreduce hook), the device does the per-particle work (qsb_cycle_init_resident);
+ *                                   _start/_source/_rr/_split go to the host model's balance.  On the first call the host
+ *                                   model's processed vault (if any) is moved to the device.
+ *   qsb_mc_cycle_tracking_resident  cycleTracking (src/main.cc:138-307) on one rank: qsb_track + tallies into the host model;
+ *                                   the census stays on the device.  Several ranks: qsb_track / exchange rounds by the
+ *                                   caller, then qsb_mc_tracking_end_resident.
+ *   qsb_mc_cycle_finalize           unchanged (src/main.cc:310-324).
+ *   qsb_mc_census_to_host           bring the census back into the host model's processed vault (end of run, census
+ *                                   output, or to continue with host-side cycles).
+ * Host and device cycles can be mixed freely; only host memory <-> device copies of the whole vault separate them. */
+int  qsb_mc_cycle_init_resident(qsb_mc* mc, qsb_ctx* ctx, qsb_cycle_init_result* result /* optional */);
+int  qsb_mc_cycle_tracking_resident(qsb_mc* mc, qsb_ctx* ctx, qsb_track_stats* stats /* optional */);
+int  qsb_mc_tracking_end_resident(qsb_mc* mc, qsb_ctx* ctx);
+int  qsb_mc_census_to_host(qsb_mc* mc, qsb_ctx* ctx);
 
 const char* qsb_version(void);
 

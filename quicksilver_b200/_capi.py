@@ -77,6 +77,19 @@ class TrackStats(C.Structure):
                 ("n_launches", C.c_uint32), ("device_ms", C.c_float)]
 
 
+class CycleInitArgs(C.Structure):
+    """qsb_cycle_init_args"""
+    _fields_ = [("plan_id", C.c_uint64), ("source_offsets", _P(C.c_int32)), ("source_tally", _P(C.c_uint64)),
+                ("source_weight", C.c_double), ("e_min", C.c_double), ("e_max", C.c_double),
+                ("split_factor", C.c_double), ("low_weight_cutoff", C.c_double)]
+
+
+class CycleInitResult(C.Structure):
+    """qsb_cycle_init_result"""
+    _fields_ = [("n_start", C.c_uint64), ("n_source", C.c_uint64), ("n_rr", C.c_uint64), ("n_split", C.c_uint64),
+                ("n_processing", C.c_uint64), ("device_ms", C.c_float), ("n_launches", C.c_uint32)]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32)
 
 
@@ -102,6 +115,13 @@ def _declare(lib):
         "qsb_mc_get_int": (C.c_int, [vp, C.c_char_p, _P(C.c_int64)]),
         "qsb_mc_get_double": (C.c_int, [vp, C.c_char_p, _P(C.c_double)]),
         "qsb_mc_cycle_init": (C.c_int, [vp]),
+        "qsb_mc_set_strict_math": (C.c_int, [vp, C.c_int]),
+        "qsb_mc_cycle_init_resident": (C.c_int, [vp, vp, _P(CycleInitResult)]),
+        "qsb_mc_cycle_tracking_resident": (C.c_int, [vp, vp, _P(TrackStats)]),
+        "qsb_mc_tracking_end_resident": (C.c_int, [vp, vp]),
+        "qsb_mc_census_to_host": (C.c_int, [vp, vp]),
+        "qsb_cycle_init_resident": (C.c_int, [vp, _P(CycleInitArgs), _P(CycleInitResult)]),
+        "qsb_put_census": (C.c_int, [vp, vp, C.c_uint64]),
         "qsb_mc_processing": (C.c_int, [vp, _P(vp), u64p]),
         "qsb_mc_processed": (C.c_int, [vp, _P(vp), u64p]),
         "qsb_mc_set_tracking_result": (C.c_int, [vp, vp, C.c_uint64, u64p, C.c_double]),

@@ -212,6 +212,16 @@ struct qsb_ctx
     uint32_t peer_epoch = 0;
     unsigned long long watchdog_ns = 0;
     PeerControl* h_peer = nullptr;              // pinned: values on their way to / back from the own control block
+    // cycleInit on the device (qsb_cycle_init_resident, cycle_init_kernels.cu)
+    const double* d_cell_volume = nullptr;               // [n_cells]
+    const unsigned long long* d_cell_id = nullptr;       // [n_cells]
+    int* d_source_offsets = nullptr;                     // [n_cells+1] the caller's source plan, kept while its plan_id stands
+    unsigned long long* d_source_tally = nullptr;        // [n_cells] running source counts, advanced on the device
+    bool have_plan = false;
+    uint64_t plan_id = 0;
+    unsigned long long plan_n_source = 0;
+    CycleInitCounters* d_init = nullptr;
+    CycleInitCounters* h_init = nullptr;                 // pinned
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
@@ -321,6 +331,8 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         im.cell_material = devUpload(image->cell_material, nc, c->owned);
         im.domain_cell_offset = devUpload(image->domain_cell_offset, (size_t)image->n_domains + 1, c->owned);
         c->d_domain_offset = im.domain_cell_offset;
+        if (image->cell_volume) c->d_cell_volume = devUpload(image->cell_volume, nc, c->owned);
+        if (image->cell_id)     c->d_cell_id = reinterpret_cast<const unsigned long long*>(devUpload(image->cell_id, nc, c->owned));
         c->host_domain_offset.assign(image->domain_cell_offset, image->domain_cell_offset + image->n_domains + 1);
 
         // hot block: energies | xs_total | xs_react | material records, one allocation, 256-byte sub-alignment
@@ -481,6 +493,7 @@ int qsb_destroy(qsb_ctx* c)
     for (void* p : c->owned) cudaFree(p);
     if (c->h_ctl) cudaFreeHost(c->h_ctl);
     if (c->h_partial) cudaFreeHost(c->h_partial);
+    if (c->h_init) cudaFreeHost(c->h_init);
     if (c->h_staging) cudaFreeHost(c->h_staging);
     if (c->h_chunk_flags) cudaFreeHost(c->h_chunk_flags);
     if (c->h_marks) cudaFreeHost(c->h_marks);
@@ -555,6 +568,142 @@ int qsb_put_particles(qsb_ctx* c, const qsb_base_particle* aos, uint64_t n)
         c->h_ctl->tail = c->host_tail;
         c->pending_inflight += n;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        return (int)QSB_OK;
+    });
+}
+
+// host AoS records -> SoA slots [first, first+n) of vault `v`, staged through the pinned bounce buffer
+static void uploadRecords(qsb_ctx* c, VaultView& v, unsigned long long first, const qsb_base_particle* aos, uint64_t n)
+{
+    const size_t chunk = c->staging_records;
+    for (uint64_t done = 0; done < n; done += chunk)
+    {
+        const uint64_t m = std::min<uint64_t>(chunk, n - done);
+        QSB_CUDA(cudaStreamSynchronize(c->stream));      // pinned staging buffer is free again
+        std::memcpy(c->h_staging, aos + done, m * sizeof(qsb_base_particle));
+        QSB_CUDA(cudaMemcpyAsync(c->staging, c->h_staging, m * sizeof(qsb_base_particle), cudaMemcpyHostToDevice, c->stream));
+        const int grid = (int)std::min<uint64_t>((m + 255) / 256, 4096);
+        aos_to_soa_kernel<<<grid, 256, 0, c->stream>>>((const qsb_base_particle*)c->staging, m, v, first + done, c->d_domain_offset, c->epoch);
+        c->launches++;
+    }
+    QSB_CUDA(cudaGetLastError());
+}
+
+int qsb_put_census(qsb_ctx* c, const qsb_base_particle* aos, uint64_t n)
+{
+    if (n && !aos) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        VaultView& v = c->vault[1 - c->proc];
+        if (n > v.capacity) { c->error = "census vault capacity exceeded by qsb_put_census"; return (int)QSB_ERR_CAPACITY; }
+        uploadRecords(c, v, 0, aos, n);
+        // from here on the context looks as if a (non-streamed) cycle had just ended with this census
+        std::memset(c->h_ctl, 0, sizeof(DevControl));
+        c->h_ctl->epoch = c->epoch;
+        c->h_ctl->census_count = n;
+        pushControl(c);
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        c->host_tail = c->ready_prefix = c->consumed = c->pending_inflight = 0;
+        c->n_in_aos = 0;
+        c->streaming = false;
+        c->in_cycle = true;
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_cycle_init_resident(qsb_ctx* c, const qsb_cycle_init_args* args, qsb_cycle_init_result* result)
+{
+    if (!args) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        const int n_cells = c->im.n_cells;
+        if (!c->d_cell_volume || !c->d_cell_id)
+        { c->error = "qsb_cycle_init_resident: the image carries no cell_volume / cell_id arrays"; return (int)QSB_ERR_STATE; }
+        if (!(args->source_weight > 0.0) || !(args->split_factor > 0.0))
+        { c->error = "qsb_cycle_init_resident: source_weight and split_factor must be positive"; return (int)QSB_ERR_ARG; }
+        // ---- last cycle's census: how many records, and that they are in the vault ----
+        unsigned long long carried = 0;
+        if (c->in_cycle)
+        {
+            if (c->streaming)
+            { c->error = "qsb_cycle_init_resident: the previous cycle's census was streamed to the host (qsb_stream_begin), not kept in the vault; "
+                         "hand it back with qsb_put_census"; return (int)QSB_ERR_STATE; }
+            pullControl(c);
+            carried = std::min<unsigned long long>(c->h_ctl->census_count, c->vault[1 - c->proc].capacity);
+        }
+        // ---- source plan ----
+        if (!c->have_plan || args->plan_id != c->plan_id)
+        {
+            if (!args->source_offsets || !args->source_tally)
+            { c->error = "qsb_cycle_init_resident: a new plan_id needs source_offsets and source_tally"; return (int)QSB_ERR_ARG; }
+            if (args->source_offsets[0] != 0) { c->error = "qsb_cycle_init_resident: source_offsets[0] must be 0"; return (int)QSB_ERR_ARG; }
+            for (int i = 0; i < n_cells; ++i)
+                if (args->source_offsets[i + 1] < args->source_offsets[i])
+                { c->error = "qsb_cycle_init_resident: source_offsets must not decrease"; return (int)QSB_ERR_ARG; }
+            if (!c->d_source_offsets)
+            {
+                c->d_source_offsets = devAlloc<int>((size_t)n_cells + 1, c->owned);
+                c->d_source_tally = devAlloc<unsigned long long>((size_t)n_cells, c->owned);
+                c->d_init = devAlloc<CycleInitCounters>(1, c->owned);
+                QSB_CUDA(cudaMallocHost((void**)&c->h_init, sizeof(CycleInitCounters)));
+            }
+            QSB_CUDA(cudaStreamSynchronize(c->stream));
+            QSB_CUDA(cudaMemcpy(c->d_source_offsets, args->source_offsets, ((size_t)n_cells + 1) * sizeof(int), cudaMemcpyHostToDevice));
+            QSB_CUDA(cudaMemcpy(c->d_source_tally, args->source_tally, (size_t)n_cells * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+            c->plan_n_source = (unsigned long long)args->source_offsets[n_cells];
+            c->plan_id = args->plan_id;
+            c->have_plan = true;
+        }
+        // ---- the cycle's clean slate (what qsb_cycle_begin does) ----
+        c->epoch++;
+        std::memset(c->h_ctl, 0, sizeof(DevControl));
+        c->h_ctl->epoch = c->epoch;
+        c->consumed = 0;
+        c->streaming = false; c->stream_input_issued = false;
+        c->n_in_aos = 0; c->host_in = nullptr; c->host_out = nullptr; c->host_out_cap = 0; c->census_copied = 0; c->next_chunk = 0;
+        pushControl(c);
+        QSB_CUDA(cudaMemsetAsync(c->flux, 0, (size_t)c->im.n_cells * c->im.n_groups * sizeof(double), c->stream));
+        QSB_CUDA(cudaMemsetAsync(c->d_init, 0, sizeof(CycleInitCounters), c->stream));
+        // ---- census + source -> population control -> roulette -> processing vault ----
+        CycleInitArgs a;
+        a.src = c->vault[1 - c->proc];
+        a.dst = c->vault[c->proc];
+        a.n_carried = carried; a.n_source = c->plan_n_source;
+        a.source_offsets = c->d_source_offsets; a.source_tally = c->d_source_tally;
+        a.cell_id = c->d_cell_id; a.cell_volume = c->d_cell_volume; a.nodes = c->im.nodes; a.n_cells = n_cells;
+        a.source_weight = args->source_weight; a.e_min = args->e_min; a.e_max = args->e_max; a.dt = c->dt;
+        a.factor = args->split_factor;
+        a.cutoff = args->low_weight_cutoff; a.weight_cutoff = args->low_weight_cutoff * args->source_weight;
+        a.epoch = c->epoch;
+        a.out = c->d_init;
+        uint32_t n_launch = 0;
+        QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
+        if (a.n_carried + a.n_source > 0)
+        {
+            launch_cycle_init(a, c->sm_count, c->stream);
+            ++n_launch;
+            if (a.n_source > 0) { launch_source_tally_advance(c->d_source_tally, c->d_source_offsets, n_cells, c->stream); ++n_launch; }
+            QSB_CUDA(cudaGetLastError());
+            c->launches += n_launch;
+        }
+        QSB_CUDA(cudaEventRecord(c->ev1, c->stream));
+        QSB_CUDA(cudaMemcpyAsync(c->h_init, c->d_init, sizeof(CycleInitCounters), cudaMemcpyDeviceToHost, c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        QSB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->in_cycle = true;
+        const unsigned long long n_out = std::min<unsigned long long>(c->h_init->n_out, a.dst.capacity);
+        c->h_ctl->tail = n_out;
+        c->host_tail = n_out;
+        c->ready_prefix = n_out;
+        c->pending_inflight = n_out;
+        QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->tail, &c->h_ctl->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        if (result)
+        {
+            result->n_start = carried; result->n_source = a.n_source;
+            result->n_rr = c->h_init->n_rr; result->n_split = c->h_init->n_split;
+            result->n_processing = n_out; result->device_ms = ms; result->n_launches = n_launch;
+        }
+        if (c->h_init->overflow || c->h_init->n_out > a.dst.capacity)
+        { c->error = "processing vault capacity exceeded by qsb_cycle_init_resident; raise qsb_options.particle_capacity"; return (int)QSB_ERR_CAPACITY; }
         return (int)QSB_OK;
     });
 }

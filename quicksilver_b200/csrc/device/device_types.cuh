@@ -198,6 +198,35 @@ struct TrackArgs
     unsigned long long watchdog_ns;     // give up (abort everywhere) when a launch has not terminated after this long
 };
 
+// cycleInit on the device (cycle_init_kernels.cu): last cycle's census + this cycle's source particles -> population control
+// -> low-weight roulette -> processing vault, one kernel
+struct CycleInitCounters
+{
+    unsigned long long n_out;           // records appended to the processing vault
+    unsigned long long n_rr;            // particles killed by population control or the low-weight roulette (Balance::_rr)
+    unsigned long long n_split;         // split copies made (Balance::_split)
+    unsigned int overflow, pad;
+};
+struct CycleInitArgs
+{
+    VaultView src;                      // census vault of the previous cycle, records [0, n_carried)
+    VaultView dst;                      // processing vault of this cycle
+    unsigned long long n_carried, n_source;
+    const int* source_offsets;          // [n_cells+1] prefix sum of the per-cell source counts
+    const unsigned long long* source_tally; // [n_cells] the cells' running source counts before this cycle
+    const unsigned long long* cell_id;  // [n_cells]
+    const double* cell_volume;          // [n_cells]
+    const double* nodes;                // [n_cells*42]
+    int n_cells;
+    double source_weight, e_min, e_max, dt;
+    double factor;                      // population-control factor (1.0: none)
+    double cutoff, weight_cutoff;       // low-weight roulette: relative cut-off (<= 0: off) and cut-off * source weight
+    uint32_t epoch;
+    CycleInitCounters* out;
+};
+void launch_cycle_init(const CycleInitArgs& a, int sm_count, cudaStream_t s);
+void launch_source_tally_advance(unsigned long long* tally, const int* offsets, int n_cells, cudaStream_t s);
+
 // launchers implemented twice in track_kernels.cu (validation: --fmad=false + strict math; fast)
 void launch_track_validation(const TrackArgs& a, int grid, int block, cudaStream_t s);
 void launch_track_fast(const TrackArgs& a, int grid, int block, cudaStream_t s);

@@ -345,7 +345,7 @@ void rouletteLowWeightParticles(MonteCarlo& mc)
 void cycleFinalize(MonteCarlo& mc, Balance& row, double& flux)
 {
     Balance& task = mc.tallies.balanceTask;
-    task[QSB_BAL_END] = mc.processed.size();
+    task[QSB_BAL_END] = mc.residentCensus ? mc.residentCensusCount : mc.processed.size();
     row = task;
     mc.reduceSum(row.v, QSB_BAL_COUNT);
     flux = mc.tallies.scalarFluxSum;

@@ -88,6 +88,9 @@ public:
     std::vector<int32_t>  sourceOffsets;            // [nCells+1] prefix sum of the per-cell source counts (flat cell order)
     std::vector<uint64_t> sourceTallyFlat;          // [nCells] scratch: per-cell running source counts handed to the device
     double                sourcePlanWeight = -1.0;  // source particle weight the plan was built for
+    double                cachedSourceWeight = 0.0, cachedSourceWeightDt = -1.0;
+    uint64_t              devicePlanId = ~0ull;      // plan id the device context `devicePlanCtx` holds
+    const void*           devicePlanCtx = nullptr;
     uint64_t              sourcePlanId = 0;         // bumped whenever the plan or the host-side tallies change under the device
 
     qsb_allreduce_fn  allreduce = nullptr;

@@ -6,7 +6,9 @@
 #include <cstring>
 #include <exception>
 #include <new>
+#include <stdexcept>
 #include <string>
+#include <climits>
 
 #include "MonteCarlo.hh"
 
@@ -109,7 +111,8 @@ int qsb_mc_get_int(qsb_mc* h, const char* key, int64_t* out)
         else if (k == "nDomains") *out = (int64_t)mc.domain.size();
         else if (k == "nCells") *out = mc.image.n_cells;
         else if (k == "nProcessing") *out = (int64_t)mc.processing.size();
-        else if (k == "nProcessed") *out = (int64_t)mc.processed.size();
+        else if (k == "nProcessed") *out = (int64_t)(mc.residentCensus ? mc.residentCensusCount : mc.processed.size());
+        else if (k == "residentCensus") *out = mc.residentCensus ? 1 : 0;
         else { mc.lastError = "unknown integer key " + k; return (int)QSB_ERR_ARG; }
         return (int)QSB_OK;
     });
@@ -138,7 +141,22 @@ int qsb_mc_get_double(qsb_mc* h, const char* key, double* out)
 
 int qsb_mc_cycle_init(qsb_mc* h)
 {
-    return guarded(h, [&](MonteCarlo& mc) { cycleInit(mc); return QSB_OK; });
+    return guarded(h, [&](MonteCarlo& mc) {
+        if (mc.residentCensus)
+        {
+            h->error = "qsb_mc_cycle_init: the census of the last cycle is resident on the device; call qsb_mc_census_to_host first "
+                       "(or continue with qsb_mc_cycle_init_resident)";
+            return (int)QSB_ERR_STATE;
+        }
+        cycleInit(mc);
+        mc.sourcePlanId++;          // the host advanced the cells' source counts: a device copy of them is stale
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_mc_set_strict_math(qsb_mc* h, int on)
+{
+    return guarded(h, [&](MonteCarlo& mc) { mc.strictMath = on != 0; return QSB_OK; });
 }
 
 int qsb_mc_processing(qsb_mc* h, const qsb_base_particle** aos, uint64_t* n)
@@ -160,6 +178,7 @@ int qsb_mc_set_tracking_result(qsb_mc* h, const qsb_base_particle* census, uint6
     return guarded(h, [&](MonteCarlo& mc) {
         mc.processed.assign(census, census + n_census);
         mc.processing.clear();
+        mc.residentCensus = false;
         static const int tracked[] = { QSB_BAL_ABSORB, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_FISSION,
                                        QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
         for (int i : tracked) mc.tallies.balanceTask[i] += balance[i];
@@ -379,6 +398,7 @@ extern "C" int qsb_mc_tracking_end(qsb_mc* h, qsb_ctx* ctx)
         }
         mc.processed.resize(n);
         mc.processing.clear();
+        mc.residentCensus = false;
         uint64_t bal[QSB_BAL_COUNT];
         double flux = 0.0;
         if ((rc = qsb_get_balance(ctx, bal)) != QSB_OK) return fail(rc);
@@ -414,4 +434,149 @@ extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* s
         std::fprintf(stderr, "[qsb] cycle_tracking: begin %.2f ms, track %.2f ms (kernel %.2f ms), end %.2f ms\n", t1 - t0, t2 - t1,
                      (double)(stats ? stats->device_ms : local.device_ms), now() - t2);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole cycle with the population resident on the device (include/qsb.h, "device-resident cycles").
+// cycleInit (src/main.cc:96-121): the host model keeps what needs the deck or other ranks -- the weight of a source
+// particle (src/MC_SourceNow.cc:41-61), the per-cell source counts that follow from it (:72-76), the split / roulette
+// factor (src/PopulationControl.cc:32-57) -- and the balance bookkeeping; the per-particle work runs on the device.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int qsb_mc_cycle_init_resident(qsb_mc* h, qsb_ctx* ctx, qsb_cycle_init_result* result)
+{
+    if (!ctx) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
+        int rc;
+        if (!mc.residentCensus)
+        {
+            // coming from host-side cycles (or the very first cycle): last cycle's census is the processed vault
+            if ((rc = qsb_put_census(ctx, mc.processed.data(), mc.processed.size())) != QSB_OK) return fail(rc);
+            mc.residentCensusCount = mc.processed.size();
+            mc.processed.clear();
+            mc.residentCensus = true;
+        }
+        mc.processing.clear();
+        mc.tallies.balanceTask[QSB_BAL_START] = mc.residentCensusCount;          // src/main.cc:106-110
+        mc.tallies.scalarFluxSum = 0.0;
+
+        // source plan: per-cell counts (int)(cellWeight / weight), flat cell order; rebuilt only when the weight changes
+        // (a function of the deck and the time step only: evaluated once, it walks every cell of every rank)
+        if (mc.cachedSourceWeightDt != mc.timeStep) { mc.cachedSourceWeight = sourceParticleWeight(mc); mc.cachedSourceWeightDt = mc.timeStep; }
+        const double weight = mc.cachedSourceWeight;
+        mc.sourceParticleWeight = weight;
+        const size_t nCells = (size_t)mc.image.n_cells;
+        if (mc.sourceOffsets.size() != nCells + 1 || weight != mc.sourcePlanWeight)
+        {
+            mc.sourceOffsets.assign(nCells + 1, 0);
+            size_t flat = 0;
+            for (const Domain& d : mc.domain)
+                for (int c = 0; c < d.nCells; ++c, ++flat)
+                {
+                    const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * mc.timeStep;
+                    const int n = (int)(cellWeight / weight);
+                    const int64_t next = (int64_t)mc.sourceOffsets[flat] + (n > 0 ? n : 0);
+                    if (next > INT32_MAX) throw std::runtime_error("more than 2^31 source particles on one rank");
+                    mc.sourceOffsets[flat + 1] = (int32_t)next;
+                }
+            mc.sourcePlanWeight = weight;
+            mc.sourcePlanId++;
+        }
+        const uint64_t nSource = (uint64_t)mc.sourceOffsets[nCells];
+
+        qsb_cycle_init_args a;
+        std::memset(&a, 0, sizeof a);
+        a.plan_id = mc.sourcePlanId;
+        a.source_offsets = mc.sourceOffsets.data();
+        // the device keeps and advances its own copy of the running source counts; it re-reads ours when the plan id moved
+        if (mc.devicePlanId != mc.sourcePlanId || mc.devicePlanCtx != (const void*)ctx)
+        {
+            mc.sourceTallyFlat.resize(nCells);
+            size_t flat = 0;
+            for (const Domain& d : mc.domain)
+                for (int c = 0; c < d.nCells; ++c, ++flat) mc.sourceTallyFlat[flat] = d.sourceTally[c];
+            a.source_tally = mc.sourceTallyFlat.data();
+            a.plan_id = ++mc.sourcePlanId;                 // a fresh id: this context has never seen it
+        }
+        a.source_weight = weight;
+        a.e_min = mc.params.simulationParams.eMin; a.e_max = mc.params.simulationParams.eMax;
+        a.split_factor = populationControlFactor(mc, mc.residentCensusCount + nSource);
+        a.low_weight_cutoff = mc.params.simulationParams.lowWeightCutoff;
+
+        qsb_cycle_init_result local;
+        qsb_cycle_init_result* r = result ? result : &local;
+        if ((rc = qsb_cycle_init_resident(ctx, &a, r)) != QSB_OK) return fail(rc);
+        mc.devicePlanId = mc.sourcePlanId; mc.devicePlanCtx = (const void*)ctx;
+        if (r->n_start != mc.residentCensusCount || r->n_source != nSource)
+        { h->error = "device census / source count differs from the host model's bookkeeping"; return (int)QSB_ERR_INTERNAL; }
+        // keep the host's own running counts in step, so that host-side cycles can take over at any time
+        {
+            size_t flat = 0;
+            for (Domain& d : mc.domain)
+                for (int c = 0; c < d.nCells; ++c, ++flat)
+                    d.sourceTally[c] += (uint64_t)(mc.sourceOffsets[flat + 1] - mc.sourceOffsets[flat]);
+        }
+        Balance& bal = mc.tallies.balanceTask;
+        bal[QSB_BAL_SOURCE] += r->n_source;
+        bal[QSB_BAL_RR] += r->n_rr;
+        bal[QSB_BAL_SPLIT] += r->n_split;
+        return (int)QSB_OK;
+    });
+}
+
+extern "C" int qsb_mc_tracking_end_resident(qsb_mc* h, qsb_ctx* ctx)
+{
+    if (!ctx) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
+        int rc;
+        uint64_t bal[QSB_BAL_COUNT];
+        double flux = 0.0;
+        uint64_t nCensus = 0;
+        if ((rc = qsb_get_balance(ctx, bal)) != QSB_OK) return fail(rc);
+        if ((rc = qsb_census_count(ctx, &nCensus)) != QSB_OK) return fail(rc);
+        if ((rc = qsb_scalar_flux_sum(ctx, &flux)) != QSB_OK) return fail(rc);
+        if (mc.params.simulationParams.coralBenchmark && (rc = qsb_fluence_accumulate(ctx)) != QSB_OK) return fail(rc);
+        static const int tracked[] = { QSB_BAL_ABSORB, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_FISSION,
+                                       QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
+        for (int i : tracked) mc.tallies.balanceTask[i] += bal[i];
+        mc.tallies.scalarFluxSum += flux;
+        mc.residentCensus = true;
+        mc.residentCensusCount = nCensus;
+        return (int)QSB_OK;
+    });
+}
+
+extern "C" int qsb_mc_cycle_tracking_resident(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* stats)
+{
+    if (!h || !ctx) return QSB_ERR_ARG;
+    qsb_track_stats local;
+    int rc = qsb_track(ctx, stats ? stats : &local);
+    if (rc != QSB_OK)
+    {
+        h->error = std::string("device: ") + qsb_last_error(ctx);
+        return rc;
+    }
+    return qsb_mc_tracking_end_resident(h, ctx);
+}
+
+extern "C" int qsb_mc_census_to_host(qsb_mc* h, qsb_ctx* ctx)
+{
+    if (!ctx) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        if (!mc.residentCensus) return (int)QSB_OK;           // it already is
+        uint64_t n = 0;
+        int rc = qsb_census_count(ctx, &n);
+        if (rc == QSB_OK)
+        {
+            mc.processed.resize(n);
+            rc = qsb_get_census(ctx, mc.processed.data(), n, &n);
+        }
+        if (rc != QSB_OK) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; }
+        mc.processed.resize(n);
+        mc.processing.clear();
+        mc.residentCensus = false;
+        mc.residentCensusCount = 0;
+        return (int)QSB_OK;
+    });
 }

@@ -44,6 +44,24 @@ class DeviceContext:
         p = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
         self._check(self._lib.qsb_put_particles(self._h, p.ctypes.data_as(C.c_void_p), len(p)))
 
+    def put_census(self, particles):
+        """host records -> census vault (the next cycle_init_resident carries them over)."""
+        p = np.ascontiguousarray(particles, dtype=PARTICLE_DTYPE)
+        self._check(self._lib.qsb_put_census(self._h, p.ctypes.data_as(C.c_void_p), len(p)))
+
+    def cycle_init_resident(self, plan_id, source_offsets, source_tally, source_weight, e_min, e_max, split_factor=1.0,
+                            low_weight_cutoff=0.0):
+        """qsb_cycle_init_resident: census vault + source particles -> population control -> roulette -> processing vault."""
+        off = None if source_offsets is None else np.ascontiguousarray(source_offsets, dtype=np.int32)
+        tal = None if source_tally is None else np.ascontiguousarray(source_tally, dtype=np.uint64)
+        args = _capi.CycleInitArgs(int(plan_id),
+                                   None if off is None else off.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   None if tal is None else tal.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                   float(source_weight), float(e_min), float(e_max), float(split_factor), float(low_weight_cutoff))
+        res = _capi.CycleInitResult()
+        self._check(self._lib.qsb_cycle_init_resident(self._h, C.byref(args), C.byref(res)))
+        return res
+
     def track(self):
         stats = _capi.TrackStats()
         self._check(self._lib.qsb_track(self._h, C.byref(stats)))

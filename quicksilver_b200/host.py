@@ -77,6 +77,30 @@ class MonteCarlo:
     def cycle_init(self):
         self._check(self._lib.qsb_mc_cycle_init(self._h))
 
+    def set_strict_math(self, on=True):
+        """MC_SourceNow's log/sin/cos: libm (default, the reference's bits) or the portable functions the device uses."""
+        self._check(self._lib.qsb_mc_set_strict_math(self._h, int(bool(on))))
+
+    # -- the cycle with the population resident on the device (include/qsb.h, "device-resident cycles") --------------
+    def cycle_init_resident(self, ctx):
+        """cycleInit with the per-particle work on the device; returns the qsb_cycle_init_result."""
+        res = _capi.CycleInitResult()
+        self._check(self._lib.qsb_mc_cycle_init_resident(self._h, ctx._h, C.byref(res)))
+        return res
+
+    def cycle_tracking_resident(self, ctx):
+        """cycleTracking on one rank, census left on the device."""
+        stats = _capi.TrackStats()
+        self._check(self._lib.qsb_mc_cycle_tracking_resident(self._h, ctx._h, C.byref(stats)))
+        return stats
+
+    def tracking_end_resident(self, ctx):
+        self._check(self._lib.qsb_mc_tracking_end_resident(self._h, ctx._h))
+
+    def census_to_host(self, ctx):
+        """bring the resident census back into the processed vault."""
+        self._check(self._lib.qsb_mc_census_to_host(self._h, ctx._h))
+
     def processing(self):
         """the processing vault (tracking input) as a structured numpy array (copy)."""
         ptr, n = C.c_void_p(), C.c_uint64()

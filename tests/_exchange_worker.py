@@ -27,7 +27,8 @@ def main():
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local))
-        sim = driver.Simulation(argv, rank, world, device=local, validation=True, dist=dist, particle_capacity=1 << 20)
+        sim = driver.Simulation(argv, rank, world, device=local, validation=True, dist=dist, particle_capacity=1 << 20,
+                                resident=os.environ.get("QSB_TEST_RESIDENT") == "1")
     else:
         dist.init_process_group("gloo")
         sim = driver.Simulation(argv, rank, world, dist=dist,

@@ -24,8 +24,9 @@ def _gpu_count():
         return 0
 
 
-def _single_rank_strict(argv, cycles):
+def _single_rank_strict(argv, cycles, strict_source=False):
     mc = host.MonteCarlo(argv)
+    mc.set_strict_math(strict_source)
     dt = mc.get_double("dt")
     gid = mc.image.array("cell_gid")
     rows, censuses = [], []
@@ -74,6 +75,36 @@ def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_c
     assert all(r["exchange"] == exchange for r in ranks), [r["exchange"] for r in ranks]
     if exchange == "peer":
         assert all(i["rounds"] == 1 for r in ranks for i in r["info"])
+    for c in range(cycles):
+        got, want = ranks[0]["rows"][c], want_rows[c]
+        assert got[:13] == want[:13], "cycle %d: %s != %s" % (c, got[:13], want[:13])
+        assert abs(got[13] - want[13]) <= 1e-11 * abs(want[13])
+        union = np.concatenate([np.load(out / ("census_c%d_r%d.npy" % (c, r))) for r in range(world)])
+        assert H.sort_particles(union).tobytes() == H.sort_particles(want_census[c]).tobytes(), "cycle %d census" % c
+
+
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange):
+    """the population stays on the GPUs from cycle to cycle (cycleInit on every device, split factor from the allreduced
+    global count); rows and census must equal the single-rank CPU chain -- host cycleInit in strict-math mode + oracle."""
+    world, (gx, gy, gz), n, per_cell, cycles = 2, (2, 1, 1), 8, 10, 3
+    if _gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    deck = decks.write_deck(decks.derive("CTS2", nSteps=cycles), str(tmp_path / "deck.inp"))
+    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * world]
+    argv1 = [str(a) for a in ["-i", deck] + sizes + ["-I", 1, "-J", 1, "-K", 1]]
+    argvN = [str(a) for a in ["-i", deck] + sizes + ["-I", gx, "-J", gy, "-K", gz]]
+    want_rows, want_census = _single_rank_strict(argv1, cycles, strict_source=True)
+    out = tmp_path / "out"
+    out.mkdir()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world,
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(H.ROOT, "tests", "_exchange_worker.py"), str(out), str(cycles)] + argvN
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
+                         env=dict(os.environ, QSB_TEST_BACKEND="device", QSB_EXCHANGE=exchange, QSB_PEER_WATCHDOG_S="20", QSB_TEST_RESIDENT="1"))
+    assert res.returncode == 0, res.stdout[-3000:]
+    ranks = [json.load(open(out / ("rank%d.json" % r))) for r in range(world)]
+    assert sum(i["sent"] for r in ranks for i in r["info"]) > 0
     for c in range(cycles):
         got, want = ranks[0]["rows"][c], want_rows[c]
         assert got[:13] == want[:13], "cycle %d: %s != %s" % (c, got[:13], want[:13])

@@ -157,3 +157,36 @@ def test_source_is_decomposition_independent(tmp_path):
     b["cell"] = gid_want[np.isin(gid_want, r1.image.array("cell_gid"))][np.argsort(mine["identifier"], kind="stable")]
     a["domain"] = b["domain"] = 0
     assert a.tobytes() == b.tobytes()
+
+
+def test_strict_math_source_is_the_libm_source_up_to_rounding(tmp_path):
+    """qsb_mc_set_strict_math: MC_SourceNow with the portable log/sin/cos the device cycle-init kernel uses.  Same streams,
+    same counts, same identifiers and seeds as the libm mode the golden fixtures pin to the reference; only the two
+    direction components that go through sin/cos and the number of mean free paths (log) may move, by a few ulp."""
+    deck = decks.derive("CTS2_1", nx=6, ny=6, nz=6, lx=6, ly=6, lz=6, nParticles=4320, nSteps=1)
+    a, b = _mc(tmp_path, deck, name="libm.inp"), _mc(tmp_path, deck, name="strict.inp")
+    b.set_strict_math(True)
+    a.cycle_init(), b.cycle_init()
+    pa, pb = a.processing(), b.processing()
+    assert len(pa) == len(pb) > 4000
+    for field in ("identifier", "random_number_seed", "coordinate", "kinetic_energy", "weight", "time_to_census", "cell", "domain"):
+        assert np.array_equal(pa[field], pb[field]), field
+    assert np.array_equal(pa["velocity"][:, 2], pb["velocity"][:, 2])            # gamma does not pass through sin/cos
+    speed = np.linalg.norm(pa["velocity"], axis=1)
+    assert np.abs(pa["velocity"] - pb["velocity"]).max() <= 4e-16 * speed.max()
+    assert np.allclose(pa["num_mean_free_paths"], pb["num_mean_free_paths"], rtol=4e-16, atol=1e-18)
+    # negative azimuths (half of all particles) go through the symmetry branch of the strict sin/cos
+    assert (pa["velocity"][:, 1] < 0).sum() > 1000
+
+
+def test_host_cycle_init_parts_agree_with_the_whole(tmp_path):
+    """the global numbers the device cycle-init is handed (source particle weight, per-cell source counts, split factor)
+    are the ones the host's own cycleInit uses: start + source + split - rr particles come out of it"""
+    deck = decks.derive("CTS2_1", nx=6, ny=6, nz=6, lx=6, ly=6, lz=6, nParticles=4320, nSteps=2)
+    mc = _mc(tmp_path, deck)
+    mc.cycle_init()
+    n = len(mc.processing())
+    # 10 % of nParticles are sourced per cycle (src/MC_SourceNow.cc:59), the population is split up to the target
+    w = mc.get_double("source_particle_weight")
+    assert w > 0
+    assert abs(n - 4320) <= 0.05 * 4320
