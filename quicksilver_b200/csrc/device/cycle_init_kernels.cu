@@ -14,9 +14,11 @@
 // order is immaterial to the tracker (SURVEY 8a note 9).
 //
 // Work item i: i < n_carried -> census particle i; otherwise source particle i - n_carried, whose cell is found by
-// bisecting the prefix sum of the per-cell source counts.  Output: a warp compacts each "round" of results (split copy k
-// of every lane, then the lanes' own particles) with a ballot and reserves the slots with one atomicAdd, so every store
-// instruction writes consecutive slots of an SoA array.  HBM-bound: reads 164 B and writes 172 B per particle.
+// bisecting the prefix sum of the per-cell source counts.  Output: every thread first counts the records its particle
+// will produce, the block reserves that many slots of the processing vault with ONE atomicAdd (10.7 M particles = 42 k
+// atomics on the fill counter, not 330 k), and each warp then writes its share "round" by round (split copy k of every
+// lane that has one, then the lanes' own particles), each round compacted with a ballot so that a store instruction
+// writes consecutive slots of an SoA array.  HBM-bound: reads 164 B and writes 168 B per particle.
 //
 // Arithmetic: qs_cycle_init.h, the very source the host model runs (pinned byte for byte against the reference by the
 // golden fixtures), compiled with --fmad=false and the portable log/sin/cos -> the device's particles equal the host
@@ -68,36 +70,63 @@ __device__ __forceinline__ void store_processing(const VaultView& v, unsigned lo
     __stcs(v.ready + i, epoch);
 }
 
-// one output round of a warp: lanes with `keep` get consecutive slots of the processing vault
+// one output round of a warp: lanes with `keep` get consecutive slots of the processing vault, starting at `base`
+// (the warp's share of the block's reservation), which moves on by the number of records written
 __device__ __forceinline__ void emit_round(const CycleInitArgs& a, unsigned lane, bool keep, const InitParticle& p, double weight,
-                                           unsigned long long seed, unsigned long long id)
+                                           unsigned long long seed, unsigned long long id, unsigned long long& base)
 {
     const unsigned mask = __ballot_sync(kFull, keep);
-    if (mask == 0u) return;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&a.out->n_out, (unsigned long long)__popc(mask));
-    base = __shfl_sync(kFull, base, 0);
-    if (!keep) return;
-    const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
-    if (slot >= a.dst.capacity) { a.out->overflow = 1u; return; }
-    store_processing(a.dst, slot, p, weight, seed, id, a.epoch);
+    if (keep)
+    {
+        const unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+        if (slot >= a.dst.capacity) a.out->overflow = 1u;
+        else store_processing(a.dst, slot, p, weight, seed, id, a.epoch);
+    }
+    base += __popc(mask);
+}
+
+// The decisions of one particle, taken from its own stream: population control (src/PopulationControl.cc:66-122, not
+// entered at all when the factor is exactly 1, :60), then for each split copy -- a copy of the re-weighted particle with
+// a stream spawned from the parent's, in order (:106-116) -- and finally for the particle itself the low-weight roulette
+// (src/PopulationControl.cc:127-171).  The walk over the copies and the particle is deterministic, so the kernel makes
+// it twice: once to count the records it will write, once to write them.
+struct Decisions
+{
+    bool alive;         // survived population control
+    int copies;
+    uint64_t seed;      // parent's stream after population control
+    double weight;      // after population control
+};
+
+__device__ __forceinline__ Decisions population_control(const CycleInitArgs& a, bool alive, const InitParticle& p)
+{
+    Decisions d;
+    d.alive = alive; d.copies = 0; d.seed = p.seed; d.weight = p.weight;
+    if (alive && a.factor != 1.0)
+    {
+        const int c = qs_population_control_one(a.factor, &d.seed, &d.weight);
+        if (c < 0) d.alive = false; else d.copies = c;
+    }
+    return d;
 }
 
 __global__ void __launch_bounds__(256) cycle_init_kernel(const __grid_constant__ CycleInitArgs a)
 {
-    const unsigned lane = threadIdx.x & 31u;
+    __shared__ unsigned long long s_warp_base[8];
+    __shared__ unsigned s_warp_count[8];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned long long n_total = a.n_carried + a.n_source;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long n_rr = 0, n_split = 0;
-    // whole warps iterate together (the loop bound is rounded up to a multiple of 32), lanes past the end stay idle
-    const unsigned long long n_round = (n_total + 31ull) & ~31ull;
+    unsigned n_rr = 0, n_split = 0;
+    // whole blocks iterate together (the loop bound is rounded up to a multiple of the block), threads past the end stay idle
+    const unsigned long long n_round = (n_total + 255ull) & ~255ull;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_round; i += stride)
     {
-        bool alive = i < n_total;
+        const bool present = i < n_total;
         InitParticle p;
         p.weight = 0.0; p.seed = 0; p.id = 0;
-        if (alive && i < a.n_carried) load_census(a.src, i, p);
-        else if (alive)
+        if (present && i < a.n_carried) load_census(a.src, i, p);
+        else if (present)
         {
             // source particle j: cell = last cell whose offset is <= j (cells without source particles are skipped)
             const unsigned long long j = i - a.n_carried;
@@ -121,43 +150,67 @@ __global__ void __launch_bounds__(256) cycle_init_kernel(const __grid_constant__
             p.tags = make_int4(QSB_EV_CENSUS, 0, 0, 0);      // last_event = census (MC_Particle's default), species 0
         }
 
-        // PopulationControlGuts (src/PopulationControl.cc:66-122); not entered at all when the factor is exactly 1 (:60)
-        int copies = 0;
-        uint64_t seed = p.seed;
-        double weight = p.weight;
-        if (alive && a.factor != 1.0)
+        const Decisions d = population_control(a, present, p);
+        if (present && !d.alive) ++n_rr;
+        n_split += (unsigned)d.copies;
+        const bool roulette = a.cutoff > 0.0;
+
+        // ---- pass 1: how many records does this particle put into the vault (itself + surviving copies) ----
+        unsigned count = 0;
+        if (d.alive)
         {
-            const int c = qs_population_control_one(a.factor, &seed, &weight);
-            if (c < 0) { alive = false; ++n_rr; }
-            else { copies = c; n_split += (unsigned long long)c; }
+            uint64_t seed = d.seed;
+            for (int k = 1; k <= d.copies; ++k)
+            {
+                uint64_t child_seed = qs_rng_spawn(&seed);
+                double child_weight = d.weight;
+                if (!roulette || qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &child_seed, &child_weight)) ++count; else ++n_rr;
+            }
+            double weight = d.weight;
+            if (!roulette || qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &seed, &weight)) ++count; else ++n_rr;
         }
-        // split copies: a copy of the (re-weighted) particle with a stream spawned from the parent's, in order (:106-116);
-        // each then meets the low-weight roulette on its own stream (src/PopulationControl.cc:127-171)
-        const int max_copies = __reduce_max_sync(kFull, alive ? copies : 0);
+        // ---- one reservation per block: warp totals -> shared memory -> a single atomicAdd on the vault's fill count ----
+        const unsigned warp_count = __reduce_add_sync(kFull, count);
+        if (lane == 0) s_warp_count[warp] = warp_count;
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            unsigned total = 0;
+            for (int w = 0; w < 8; ++w) total += s_warp_count[w];
+            unsigned long long base = total ? atomicAdd(&a.out->n_out, (unsigned long long)total) : 0ull;
+            for (int w = 0; w < 8; ++w) { s_warp_base[w] = base; base += s_warp_count[w]; }
+        }
+        __syncthreads();
+        unsigned long long base = s_warp_base[warp];
+        // ---- pass 2: the same walk again, writing.  Round k of a warp = copy k of every lane that has one, then the
+        //      lanes' own particles: each round is compacted with a ballot, so a store instruction writes consecutive slots ----
+        const int max_copies = __reduce_max_sync(kFull, d.alive ? d.copies : 0);
+        uint64_t seed = d.seed;
         for (int k = 1; k <= max_copies; ++k)
         {
-            bool keep = alive && k <= copies;
-            uint64_t child_seed = 0;
-            double child_weight = weight;
-            uint64_t child_id = 0;
+            bool keep = d.alive && k <= d.copies;
+            uint64_t child_seed = 0, child_id = 0;
+            double child_weight = d.weight;
             if (keep)
             {
                 child_seed = qs_rng_spawn(&seed);
                 child_id = child_seed;
-                if (a.cutoff > 0.0 && !qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &child_seed, &child_weight)) { keep = false; ++n_rr; }
+                if (roulette && !qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &child_seed, &child_weight)) keep = false;
             }
-            emit_round(a, lane, keep, p, child_weight, child_seed, child_id);
+            emit_round(a, lane, keep, p, child_weight, child_seed, child_id, base);
         }
-        // the particle itself
-        if (alive && a.cutoff > 0.0 && !qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &seed, &weight)) { alive = false; ++n_rr; }
-        emit_round(a, lane, alive, p, weight, seed, p.id);
+        bool keep = d.alive;
+        double weight = d.weight;
+        if (keep && roulette && !qs_roulette_low_weight_one(a.cutoff, a.weight_cutoff, &seed, &weight)) keep = false;
+        emit_round(a, lane, keep, p, weight, seed, p.id, base);
+        // (s_warp_count / s_warp_base are rewritten only after the next iteration's first barrier / between its two barriers)
     }
-    n_rr = __reduce_add_sync(kFull, (unsigned)n_rr);          // per-thread counts are tiny (items per thread x copies)
-    n_split = __reduce_add_sync(kFull, (unsigned)n_split);
+    n_rr = __reduce_add_sync(kFull, n_rr);          // per-thread counts are tiny (items per thread x copies)
+    n_split = __reduce_add_sync(kFull, n_split);
     if (lane == 0)
     {
-        if (n_rr) atomicAdd(&a.out->n_rr, n_rr);
-        if (n_split) atomicAdd(&a.out->n_split, n_split);
+        if (n_rr) atomicAdd(&a.out->n_rr, (unsigned long long)n_rr);
+        if (n_split) atomicAdd(&a.out->n_split, (unsigned long long)n_split);
     }
 }
 

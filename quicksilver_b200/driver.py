@@ -405,16 +405,19 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
     whole = {"host_staged": {"cycle_init_ms": 1e3 * host_init_s / max(args.steps, 1), "cycle_tracking_ms": 1e3 * e2e_s / max(args.steps, 1),
                              "cycle_finalize_ms": 1e3 * host_final_s / max(args.steps, 1)}}
     import os
-    if not getattr(args, "resident_only", 0) and os.environ.get("QSB_BENCH_RESIDENT", "1") != "0":
+    want_resident = os.environ.get("QSB_BENCH_RESIDENT", "1")          # "0": skip; "force": also in --resident-only (ncu) runs
+    if want_resident != "0" and (not getattr(args, "resident_only", 0) or want_resident == "force"):
         try:
-            n_res = max(2, min(args.steps, 5))
+            n_res = 20                                       # ~0.4 s of back-to-back cycles at benchmark size
             r_init = r_track = r_final = r_init_dev = r_track_dev = 0.0
             r_segments = 0
             r_launches0 = 0
+            r_sampler = ClockSampler(local_rank, 50)           # back-to-back cycles keep the GPU busy: clocks under sustained load
             for k in range(1 + n_res):                       # the first one moves the census to the device: not timed
                 barrier()
                 if k == 1:
                     r_launches0 = ctx.launch_count()
+                    r_sampler.start()
                 t0 = time.perf_counter()
                 res = mc.cycle_init_resident(ctx)
                 t1 = time.perf_counter()
@@ -434,6 +437,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
                     r_init += t1 - t0; r_track += t2 - t1; r_final += t3 - t2
                     r_init_dev += res.device_ms * 1e-3; r_track_dev += track_dev_ms * 1e-3
                     r_segments += int(row[BAL["num_segments"]])
+            r_clocks = r_sampler.stop()
             rt = torch.tensor([r_init, r_track, r_final, r_init + r_track + r_final], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(rt, op=dist.ReduceOp.MAX)
@@ -444,9 +448,31 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
                                  "segments_per_s_tracking": r_segments / r_track if r_track > 0 else 0.0,
                                  "cycle_init_kernel_ms_rank0": 1e3 * r_init_dev / n_res, "track_kernel_ms_rank0": 1e3 * r_track_dev / n_res,
                                  "gpu_launches": ctx.launch_count() - r_launches0,
-                                 "pcie_bytes_per_cycle": BAL_COUNT * 8 + 8 + 48,
+                                 "pcie_bytes_per_cycle": BAL_COUNT * 8 + 8 + 48, "clocks": r_clocks,
                                  "note": "wall clock per rank around each stage, max over ranks; population resident in HBM, source + population "
                                          "control + low-weight roulette in one kernel on the device"}
+            if os.environ.get("QSB_BENCH_RESIDENT_CHECK") and world == 1:
+                # diagnostic: the SAME population taken back through the host path (census -> host, host cycleInit, vault
+                # uploaded, tracking kernel timed alone) -- separates "the resident vault is laid out differently" from
+                # "the population of these later cycles tracks differently"
+                check = []
+                for _ in range(3):
+                    mc.census_to_host(ctx)
+                    mc.cycle_init()
+                    sim.backend.begin(mc.processing())
+                    st = ctx.track()
+                    check.append(st.device_ms)
+                    census, balance, flux_sum = sim.backend.results()
+                    mc.set_tracking_result(census, balance, flux_sum)
+                    row, _ = mc.cycle_finalize()
+                    rows.append([int(v) for v in row])
+                    # and one resident cycle on top of that host-built census
+                    res = mc.cycle_init_resident(ctx)
+                    st = mc.cycle_tracking_resident(ctx)
+                    check.append(-st.device_ms)
+                    row, _ = mc.cycle_finalize()
+                    rows.append([int(v) for v in row])
+                whole["resident"]["check_track_kernel_ms_host_built_vault_then_resident(negative)"] = check
         except Exception as e:          # an extra; the FOM line above never depends on it
             whole["resident"] = {"error": "%s: %s" % (type(e).__name__, e)}
     hs = whole["host_staged"]
