@@ -194,6 +194,9 @@ def main():
             "gpu_launches": result["gpu_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": result.get("traffic"), "peak_source": peak_src, "kernel": "track_kernel",
+                         # what the kernel really moves: ncu DRAM bytes of one full-size launch / this run's launch time
+                         "dram_achieved": (result["traffic"] / (1e-3 * result["tracking_ms_per_step_rank0"]["cuda_events_on_kernel_stream"]) / 1e9)
+                                          if result.get("traffic") and world == 1 else None,
                          "algorithmic_bytes_per_segment": w["b_seg"],
                          "algorithmic_bytes_per_launch": w["b_seg"] * result["segments_rank0"] / max(args.steps, 1),
                          "note": "achieved = SURVEY 8(d) yardstick (bytes the REFERENCE's data model touches per segment) x segments / kernel time; "
@@ -203,6 +206,16 @@ def main():
             "tracking_ms_per_step_rank0": result["tracking_ms_per_step_rank0"],
             "whole_cycle": result.get("whole_cycle"),
             "balance_check": result["balance_check"]}
+    if line["roofline"]["dram_achieved"]:
+        line["roofline"]["dram_frac"] = line["roofline"]["dram_achieved"] / peak
+    wc = result.get("whole_cycle") or {}
+    if isinstance(wc.get("resident"), dict) and wc["resident"].get("cycle_init_kernel_ms_rank0"):
+        # the HBM-bound kernel of the resident cycle: 164 B read + 168 B written per particle
+        r = wc["resident"]
+        n_part = result["h2d_bytes_per_step"] / 136.0
+        gbs = n_part * 332.0 / (r["cycle_init_kernel_ms_rank0"] * 1e-3) / 1e9
+        r["cycle_init_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "kernel": "cycle_init_kernel",
+                                    "algorithmic_bytes_per_particle": 332, "particles_per_launch": n_part}
     if args.cpu_baseline and world == 1:
         try:
             value, threads, sample, _, wall = run_reference(args.workload, 5, 1)
