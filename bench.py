@@ -35,6 +35,10 @@ WORKLOADS = {
     "Coral2_P1": dict(deck="Coral2_P1", n=64, cell_len=1.0, particles=10485760, b_seg=2270.0),
     "Coral2_P2": dict(deck="Coral2_P2", n=44, cell_len=1.0 / 11.0, particles=3407360, b_seg=1930.0),
     "CTS2": dict(deck="CTS2", n=64, cell_len=1.0, particles=2621440, b_seg=2270.0),
+    # SURVEY 8(d) input 2: one material, flat cross sections, the two opposite event mixes (97 % collisions / 71 % facet
+    # crossings), 32^3 cells of a 100 cm box, 3 276 800 particles; B_seg from the same formula (P_c = 0.97 / 0.29, L = 45.5)
+    "Homogeneous_v5": dict(deck="Homogeneous_v5", n=32, cell_len=100.0 / 32.0, particles=3276800, b_seg=2258.0),
+    "Homogeneous_v7": dict(deck="Homogeneous_v7", n=32, cell_len=100.0 / 32.0, particles=3276800, b_seg=1970.0),
 }
 GRID_LADDER = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 # the reference's CPU run is timed on a bounded sample of the same deck: its own literal single-rank size
@@ -42,6 +46,8 @@ REFERENCE_SAMPLE = {
     "Coral2_P1": dict(n=16, particles=163840),
     "Coral2_P2": dict(n=11, particles=53240),
     "CTS2": dict(n=16, particles=40960),
+    "Homogeneous_v5": dict(n=16, particles=40960),
+    "Homogeneous_v7": dict(n=16, particles=40960),
 }
 
 

@@ -162,6 +162,18 @@ int  qsb_mc_set_tracking_result(qsb_mc* mc, const qsb_base_particle* census, uin
  * row[0..12] = this cycle's global balance in QSB_BAL_* order, *flux = global scalar-flux sum. */
 int  qsb_mc_cycle_finalize(qsb_mc* mc, uint64_t row[QSB_BAL_COUNT], double* flux);
 int  qsb_mc_cumulative_balance(qsb_mc* mc, uint64_t out[QSB_BAL_COUNT]);
+/* EnergySpectrum (src/EnergySpectrum.cc:12-62; kept only when the deck or `-e` names a spectrum file): per group edge,
+ * the number of census particles the cycles so far left in that group (every cycle's census counts,
+ * Tallies::CycleFinalize src/Tallies.cc:97).  qsb_mc_energy_spectrum: n_groups+1 counts summed over ranks (every rank
+ * calls it); qsb_mc_write_energy_spectrum = PrintSpectrum: rank 0 writes <name>.dat, "index\tenergy\tcount" per line.
+ * (The reference allocates n_groups counters but reduces and prints n_groups + 1, src/MonteCarlo.cc:39-48 vs
+ * src/EnergySpectrum.cc:41-56: its last line is a read past the end.  Here the last counter is what the index means,
+ * particles above eMax -- always 0 for the reference decks; all other lines equal the reference's.) */
+int  qsb_mc_energy_spectrum(qsb_mc* mc, uint64_t* counts, uint64_t cap, uint64_t* n);
+int  qsb_mc_write_energy_spectrum(qsb_mc* mc);
+/* checkCrossSections (src/initMC.cc:392-484): per group the absorption / fission / scatter cross section of every material;
+ * written to <crossSectionsOut>.dat by qsb_mc_create when the deck or `-S` names a file; this returns the same text. */
+int  qsb_mc_cross_sections_text(qsb_mc* mc, char* buf, uint64_t cap, uint64_t* needed);
 /* one line of the reference's cycle table (src/Tallies.cc:123-144, src/Tallies.hh:60-76). */
 /* coralBenchmarkCorrectness (src/CoralBenchmark.cc:17-226): the reference's end-of-run self checks for the CORAL decks --
  * reaction ratios, collisions vs facet crossings, lost particles (all from the cumulative balance) and fluence homogeneity
@@ -270,6 +282,10 @@ int  qsb_scalar_flux_sum(qsb_ctx* ctx, double* sum);
  * flux, summed over groups, to the running per-cell fluence -- on the device, before the next qsb_cycle_begin clears the
  * flux; qsb_get_fluence copies the n_cells running totals to the host. */
 int  qsb_fluence_accumulate(qsb_ctx* ctx);
+/* EnergySpectrum::UpdateSpectrum (src/EnergySpectrum.cc:12-35) for a census that stays on the device: counts[g] = number
+ * of records of the current census whose kinetic energy lies in group g (NuclearData::getEnergyGroup,
+ * src/NuclearData.cc:208-227); n_counts must be n_groups + 1.  One histogram kernel over the census energies. */
+int  qsb_census_energy_spectrum(qsb_ctx* ctx, uint64_t* counts, uint64_t n_counts);
 int  qsb_get_fluence(qsb_ctx* ctx, double* out /* [n_cells] */);
 /* boundary-particle exchange (src/MC_Facet_Crossing_Event.cc:49-67, src/MC_Particle_Buffer.cc): the
  * tracker packs leavers into per-peer slabs of qsb_base_particle + direction cosine (160 B records);

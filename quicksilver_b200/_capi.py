@@ -147,6 +147,10 @@ def _declare(lib):
         "qsb_get_scalar_flux": (C.c_int, [vp, _P(C.c_double)]),
         "qsb_scalar_flux_sum": (C.c_int, [vp, _P(C.c_double)]),
         "qsb_fluence_accumulate": (C.c_int, [vp]),
+        "qsb_census_energy_spectrum": (C.c_int, [vp, u64p, C.c_uint64]),
+        "qsb_mc_energy_spectrum": (C.c_int, [vp, u64p, C.c_uint64, u64p]),
+        "qsb_mc_write_energy_spectrum": (C.c_int, [vp]),
+        "qsb_mc_cross_sections_text": (C.c_int, [vp, C.c_char_p, C.c_uint64, u64p]),
         "qsb_get_fluence": (C.c_int, [vp, _P(C.c_double)]),
         "qsb_send_counts": (C.c_int, [vp, u64p]),
         "qsb_send_slab": (C.c_int, [vp, C.c_int, _P(vp), u64p]),

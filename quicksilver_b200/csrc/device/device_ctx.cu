@@ -156,6 +156,40 @@ __global__ void fluence_accumulate_kernel(const double* __restrict__ flux, int n
     }
 }
 
+// EnergySpectrum::UpdateSpectrum (src/EnergySpectrum.cc:12-35) over a census in device memory: energy group of every record
+// (NuclearData::getEnergyGroup, src/NuclearData.cc:208-227, the reference's bisection on the same doubles), counted in a
+// per-block shared-memory histogram, flushed with one atomic per non-empty bin per block.  `energy` + i * stride_doubles
+// addresses record i's kinetic energy: stride 1 for the SoA census vault, 17 for the 136-byte records of a streamed census.
+__global__ void census_energy_histogram_kernel(const double* __restrict__ energy, unsigned long long n, int stride_doubles,
+                                               const double* __restrict__ edges, int n_edges, unsigned long long* __restrict__ hist)
+{
+    extern __shared__ unsigned int s_hist[];
+    for (int b = threadIdx.x; b < n_edges; b += blockDim.x) s_hist[b] = 0u;
+    __syncthreads();
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        const double e = __ldcs(energy + i * (unsigned long long)stride_doubles);
+        int group;
+        if (e <= __ldg(edges)) group = 0;
+        else if (e > __ldg(edges + n_edges - 1)) group = n_edges - 1;
+        else
+        {
+            int low = 0, high = n_edges - 1;
+            while (high != low + 1)
+            {
+                const int mid = (high + low) / 2;
+                if (e < __ldg(edges + mid)) high = mid; else low = mid;
+            }
+            group = low;
+        }
+        atomicAdd(&s_hist[group], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_edges; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&hist[b], (unsigned long long)s_hist[b]);
+}
+
 struct qsb_ctx
 {
     int device = 0;
@@ -220,6 +254,7 @@ struct qsb_ctx
     bool have_plan = false;
     uint64_t plan_id = 0;
     unsigned long long plan_n_source = 0;
+    unsigned long long* d_spectrum = nullptr;            // [n_groups+1] scratch of qsb_census_energy_spectrum
     CycleInitCounters* d_init = nullptr;
     CycleInitCounters* h_init = nullptr;                 // pinned
     uint32_t epoch = 0;
@@ -1234,6 +1269,34 @@ int qsb_fluence_accumulate(qsb_ctx* c)
         fluence_accumulate_kernel<<<grid, 256, 0, c->stream>>>(c->flux, c->im.n_cells, c->im.n_groups, c->fluence);
         c->launches++;
         QSB_CUDA(cudaGetLastError());
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_census_energy_spectrum(qsb_ctx* c, uint64_t* counts, uint64_t n_counts)
+{
+    if (!counts) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        const int n_edges = c->im.n_groups + 1;
+        if (n_counts != (uint64_t)n_edges) { c->error = "qsb_census_energy_spectrum: n_counts must be n_groups + 1"; return (int)QSB_ERR_ARG; }
+        if ((size_t)n_edges * sizeof(unsigned int) > 48 * 1024) { c->error = "qsb_census_energy_spectrum: more than 12287 energy groups"; return (int)QSB_ERR_ARG; }
+        if (!c->in_cycle) { std::memset(counts, 0, n_counts * sizeof(uint64_t)); return (int)QSB_OK; }
+        pullControl(c);
+        const unsigned long long n = std::min<unsigned long long>(c->h_ctl->census_count, c->vault[1 - c->proc].capacity);
+        if (!c->d_spectrum) c->d_spectrum = devAlloc<unsigned long long>((size_t)n_edges, c->owned);
+        QSB_CUDA(cudaMemsetAsync(c->d_spectrum, 0, (size_t)n_edges * sizeof(unsigned long long), c->stream));
+        if (n)
+        {
+            const double* energy = c->streaming ? reinterpret_cast<const double*>(c->d_census_aos) + 6 : c->vault[1 - c->proc].energy;
+            const int stride = c->streaming ? (int)(sizeof(qsb_base_particle) / sizeof(double)) : 1;
+            const int grid = (int)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)c->sm_count * 8);
+            census_energy_histogram_kernel<<<grid, 256, (size_t)n_edges * sizeof(unsigned int), c->stream>>>(energy, n, stride, c->im.energies, n_edges, c->d_spectrum);
+            c->launches++;
+            QSB_CUDA(cudaGetLastError());
+        }
+        static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "counter width");
+        QSB_CUDA(cudaMemcpyAsync(counts, c->d_spectrum, (size_t)n_edges * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        QSB_CUDA(cudaStreamSynchronize(c->stream));
         return (int)QSB_OK;
     });
 }

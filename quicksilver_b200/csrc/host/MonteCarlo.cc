@@ -2,7 +2,9 @@
 #include "MonteCarlo.hh"
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 
 #include "../qs_rng.h"
@@ -72,6 +74,18 @@ MonteCarlo::MonteCarlo(const Parameters& p, int rank_, int nRanks_)
     initNuclearData(params, nuclearData, materialDatabase);
     initMesh(params, materialDatabase, rank, nRanks, ddc, domain);
     buildImage();
+    tallies.censusEnergySpectrum.assign(nuclearData.energies.size(), 0);
+    // checkCrossSections (src/initMC.cc:72,392-484): plot data of the cross sections, when a file is named
+    if (!params.simulationParams.crossSectionsOut.empty() && rank == 0)
+    {
+        const std::string name = params.simulationParams.crossSectionsOut + ".dat";
+        if (FILE* f = std::fopen(name.c_str(), "w"))
+        {
+            const std::string text = crossSectionsText(*this);
+            std::fwrite(text.data(), 1, text.size(), f);
+            std::fclose(f);
+        }
+    }
 }
 
 // Flatten mesh + nuclear data into the arrays of qsb_image (see include/qsb.h for the layout).
@@ -344,6 +358,14 @@ void rouletteLowWeightParticles(MonteCarlo& mc)
 
 void cycleFinalize(MonteCarlo& mc, Balance& row, double& flux)
 {
+    // EnergySpectrum::UpdateSpectrum (src/Tallies.cc:97, src/EnergySpectrum.cc:12-35): every particle still held at the end
+    // of the cycle -- the census -- counts in its energy group.  A census resident on the device was histogrammed there.
+    if (!mc.params.simulationParams.energySpectrum.empty() && !mc.tallies.spectrumDoneThisCycle)
+    {
+        for (const qsb_base_particle& p : mc.processing) mc.tallies.censusEnergySpectrum[mc.nuclearData.getEnergyGroup(p.kinetic_energy)]++;
+        for (const qsb_base_particle& p : mc.processed)  mc.tallies.censusEnergySpectrum[mc.nuclearData.getEnergyGroup(p.kinetic_energy)]++;
+    }
+    mc.tallies.spectrumDoneThisCycle = false;
     Balance& task = mc.tallies.balanceTask;
     task[QSB_BAL_END] = mc.residentCensus ? mc.residentCensusCount : mc.processed.size();
     row = task;
@@ -353,6 +375,75 @@ void cycleFinalize(MonteCarlo& mc, Balance& row, double& flux)
     mc.tallies.balanceCumulative.add(row);
     task.reset();
     mc.cycle++;
+}
+
+std::vector<uint64_t> globalEnergySpectrum(const MonteCarlo& mc)
+{
+    std::vector<uint64_t> sum = mc.tallies.censusEnergySpectrum;
+    if (!sum.empty()) mc.reduceSum(sum.data(), (int)sum.size());
+    return sum;
+}
+
+std::string energySpectrumText(const MonteCarlo& mc, const std::vector<uint64_t>& global)
+{
+    std::string out;
+    char line[128];
+    for (size_t i = 0; i < mc.nuclearData.energies.size() && i < global.size(); ++i)
+    {
+        std::snprintf(line, sizeof line, "%d\t%g\t%llu\n", (int)i, mc.nuclearData.energies[i], (unsigned long long)global[i]);
+        out += line;
+    }
+    return out;
+}
+
+std::string crossSectionsText(const MonteCarlo& mc)
+{
+    const NuclearData& nd = mc.nuclearData;
+    const int nGroups = (int)nd.energies.size() - 1;
+    struct XcData { double absorption = 0., fission = 0., scatter = 0.; };
+    std::map<std::string, std::vector<XcData> > table;          // the reference keys a std::map by material name: name order
+    for (const Material& m : mc.materialDatabase.mat)
+    {
+        std::vector<XcData>& xc = table[m.name];
+        xc.resize(nGroups);
+        const unsigned nIsotopes = (unsigned)m.isoGid.size();
+        for (unsigned i = 0; i < nIsotopes; ++i)
+        {
+            const Isotope& iso = nd.isotopes[m.isoGid[i]];
+            for (int r = 0; r < iso.nReactions; ++r)
+                for (int g = 0; g < nGroups; ++g)
+                {
+                    const double v = nd.sigmaOf(m.isoGid[i], r, g) / nIsotopes;
+                    switch (iso.reactionType[r])
+                    {
+                        case QSB_REACT_SCATTER:    xc[g].scatter += v; break;
+                        case QSB_REACT_ABSORPTION: xc[g].absorption += v; break;
+                        case QSB_REACT_FISSION:    xc[g].fission += v; break;
+                        default: break;
+                    }
+                }
+        }
+    }
+    std::string out = "#group  energy";
+    char buf[256];
+    for (const auto& kv : table)
+    {
+        std::snprintf(buf, sizeof buf, "  %s_a  %s_f  %s_s", kv.first.c_str(), kv.first.c_str(), kv.first.c_str());
+        out += buf;
+    }
+    out += "\n";
+    for (int g = 0; g < nGroups; ++g)
+    {
+        std::snprintf(buf, sizeof buf, "%u  %g", (unsigned)g, (nd.energies[g] + nd.energies[g + 1]) / 2.0);
+        out += buf;
+        for (const auto& kv : table)
+        {
+            std::snprintf(buf, sizeof buf, "  %g  %g  %g", kv.second[g].absorption, kv.second[g].fission, kv.second[g].scatter);
+            out += buf;
+        }
+        out += "\n";
+    }
+    return out;
 }
 
 } // namespace qsb

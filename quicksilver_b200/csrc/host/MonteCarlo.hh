@@ -58,6 +58,10 @@ struct Tallies
     Balance balanceTask;          // this cycle (replications are summed on the device)
     Balance balanceCumulative;
     double  scalarFluxSum = 0.0;  // this cycle, local
+    // EnergySpectrum (src/EnergySpectrum.hh:9-21): per energy-group edge, how many census particles every cycle left in that
+    // group, summed over the cycles; only kept when the deck / command line names a spectrum file
+    std::vector<uint64_t> censusEnergySpectrum;   // [nGroups+1], local
+    bool spectrumDoneThisCycle = false;           // the resident path histograms the census on the device before finalize
 };
 
 class MonteCarlo
@@ -126,6 +130,11 @@ void populationControl(MonteCarlo& mc);
 void rouletteLowWeightParticles(MonteCarlo& mc);
 // src/main.cc:310-324 + src/Tallies.cc:25-98.  Returns this cycle's global balance and flux sum.
 void cycleFinalize(MonteCarlo& mc, Balance& globalRow, double& globalFlux);
+// EnergySpectrum::PrintSpectrum (src/EnergySpectrum.cc:37-62): global counts; the text of <energySpectrum>.dat
+std::vector<uint64_t> globalEnergySpectrum(const MonteCarlo& mc);
+std::string energySpectrumText(const MonteCarlo& mc, const std::vector<uint64_t>& global);
+// checkCrossSections (src/initMC.cc:392-484): the text of <crossSectionsOut>.dat
+std::string crossSectionsText(const MonteCarlo& mc);
 
 } // namespace qsb
 #endif

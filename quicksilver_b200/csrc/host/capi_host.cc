@@ -8,6 +8,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include <climits>
 
 #include "MonteCarlo.hh"
@@ -195,6 +196,43 @@ int qsb_mc_cycle_finalize(qsb_mc* h, uint64_t row[QSB_BAL_COUNT], double* flux)
         if (row) std::memcpy(row, r.v, sizeof(r.v));
         if (flux) *flux = f;
         return QSB_OK;
+    });
+}
+
+int qsb_mc_energy_spectrum(qsb_mc* h, uint64_t* counts, uint64_t cap, uint64_t* n)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        const std::vector<uint64_t> g = globalEnergySpectrum(mc);
+        if (n) *n = g.size();
+        if (counts) { if (cap < g.size()) { h->error = "spectrum buffer too small"; return (int)QSB_ERR_CAPACITY; } std::memcpy(counts, g.data(), g.size() * sizeof(uint64_t)); }
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_mc_write_energy_spectrum(qsb_mc* h)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        const std::string& name = mc.params.simulationParams.energySpectrum;
+        if (name.empty()) return (int)QSB_OK;                         // src/EnergySpectrum.cc:39
+        const std::vector<uint64_t> g = globalEnergySpectrum(mc);    // every rank reduces, rank 0 writes
+        if (mc.rank != 0) return (int)QSB_OK;
+        const std::string file = name + ".dat";
+        FILE* f = std::fopen(file.c_str(), "w");
+        if (!f) { h->error = "cannot write " + file; return (int)QSB_ERR_INPUT; }
+        const std::string text = energySpectrumText(mc, g);
+        std::fwrite(text.data(), 1, text.size(), f);
+        std::fclose(f);
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_mc_cross_sections_text(qsb_mc* h, char* buf, uint64_t cap, uint64_t* needed)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        const std::string s = crossSectionsText(mc);
+        if (needed) *needed = s.size() + 1;
+        if (buf && cap) std::snprintf(buf, cap, "%s", s.c_str());
+        return (int)QSB_OK;
     });
 }
 
@@ -537,6 +575,14 @@ extern "C" int qsb_mc_tracking_end_resident(qsb_mc* h, qsb_ctx* ctx)
         if ((rc = qsb_census_count(ctx, &nCensus)) != QSB_OK) return fail(rc);
         if ((rc = qsb_scalar_flux_sum(ctx, &flux)) != QSB_OK) return fail(rc);
         if (mc.params.simulationParams.coralBenchmark && (rc = qsb_fluence_accumulate(ctx)) != QSB_OK) return fail(rc);
+        if (!mc.params.simulationParams.energySpectrum.empty())
+        {
+            // EnergySpectrum::UpdateSpectrum (src/EnergySpectrum.cc:12-35) over a census that stays on the device
+            std::vector<uint64_t> hist(mc.tallies.censusEnergySpectrum.size(), 0);
+            if ((rc = qsb_census_energy_spectrum(ctx, hist.data(), hist.size())) != QSB_OK) return fail(rc);
+            for (size_t i = 0; i < hist.size(); ++i) mc.tallies.censusEnergySpectrum[i] += hist[i];
+            mc.tallies.spectrumDoneThisCycle = true;
+        }
         static const int tracked[] = { QSB_BAL_ABSORB, QSB_BAL_CENSUS, QSB_BAL_ESCAPE, QSB_BAL_COLLISION, QSB_BAL_FISSION,
                                        QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
         for (int i : tracked) mc.tallies.balanceTask[i] += bal[i];

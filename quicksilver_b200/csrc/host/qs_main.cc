@@ -78,6 +78,7 @@ int main(int argc, char** argv)
         std::vector<char> report(8192);
         qsb_mc_coral_benchmark_report(mc, fluence.data(), fluence.size(), report.data(), report.size(), nullptr, nullptr);
         std::printf("%s", report.data());
+        qsb_mc_write_energy_spectrum(mc);          // src/main.cc:93 (nothing unless -e / energySpectrum names a file)
         char fom[256];
         qsb_mc_format_figure_of_merit(mc, t_track_total, fom, sizeof fom);
         std::printf("%s", fom);

@@ -112,6 +112,12 @@ class DeviceContext:
     def fluence_accumulate(self):
         self._check(self._lib.qsb_fluence_accumulate(self._h))
 
+    def census_energy_spectrum(self):
+        """histogram of the current census over the energy groups (n_groups + 1 counts), computed on the device."""
+        out = np.zeros(self.image.n_groups + 1, dtype=np.uint64)
+        self._check(self._lib.qsb_census_energy_spectrum(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), len(out)))
+        return out
+
     def get_fluence(self):
         out = np.zeros(self.image.n_cells)
         self._check(self._lib.qsb_get_fluence(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))

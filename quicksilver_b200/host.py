@@ -153,6 +153,26 @@ class MonteCarlo:
         self._check(self._lib.qsb_mc_cumulative_balance(self._h, row.ctypes.data_as(C.POINTER(C.c_uint64))))
         return row
 
+    def energy_spectrum(self):
+        """EnergySpectrum: per group edge, census particles counted so far (summed over ranks; every rank calls it)."""
+        n = C.c_uint64()
+        self._check(self._lib.qsb_mc_energy_spectrum(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint64)
+        self._check(self._lib.qsb_mc_energy_spectrum(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n.value, None))
+        return out
+
+    def write_energy_spectrum(self):
+        """PrintSpectrum (src/EnergySpectrum.cc:37-62): rank 0 writes <energySpectrum>.dat; nothing if no file is named."""
+        self._check(self._lib.qsb_mc_write_energy_spectrum(self._h))
+
+    def cross_sections_text(self):
+        """checkCrossSections (src/initMC.cc:392-484): the text of <crossSectionsOut>.dat."""
+        need = C.c_uint64()
+        self._check(self._lib.qsb_mc_cross_sections_text(self._h, None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(self._lib.qsb_mc_cross_sections_text(self._h, buf, need.value, None))
+        return buf.value.decode()
+
     def coral_benchmark_report(self, fluence=None):
         """coralBenchmarkCorrectness (src/CoralBenchmark.cc): (report text -- empty unless the deck sets coralBenchmark,
         and on ranks other than 0 --, number of tests passed out of 4).  fluence: this rank's per-cell fluence."""

@@ -21,6 +21,9 @@ CASES = {
     "p2_small": ("Coral2_P2_1", dict(nx=6, ny=6, nz=6, lx=0.5454545454545454, ly=0.5454545454545454, lz=0.5454545454545454,
                                      nParticles=8640, nSteps=2), 2),
     "nofission_octant": ("NoFission", dict(nParticles=20000, nSteps=2), 2),
+    # the two opposite event mixes of SURVEY 8(d) input 2: 97 % collisions (v5) / 71 % facet crossings (v7)
+    "homogeneous_v5": ("Homogeneous_v5", dict(nx=8, ny=8, nz=8, lx=25, ly=25, lz=25, nParticles=5120, nSteps=2), 2),
+    "homogeneous_v7": ("Homogeneous_v7", dict(nx=8, ny=8, nz=8, lx=25, ly=25, lz=25, nParticles=5120, nSteps=2), 2),
     "nonflat_supercritical": ("NonFlatXC", dict(nParticles=20000, nSteps=2, dt=5e-10), 2),
 }
 

@@ -141,3 +141,52 @@ def test_resident_init_refuses_a_streamed_census(tmp_path):
     assert int(res.n_start) > 0
     ctx.close()
     mc.close()
+
+
+def _reference_groups(edges, energy):
+    """NuclearData::getEnergyGroup (src/NuclearData.cc:208-227) for an array of energies"""
+    n = len(edges)
+    g = np.clip(np.searchsorted(edges, energy, side="right") - 1, 0, n - 2)
+    g = np.where(energy <= edges[0], 0, g)
+    return np.where(energy > edges[-1], n - 1, g)
+
+
+def test_energy_spectrum_of_a_resident_census(tmp_path):
+    """EnergySpectrum (src/EnergySpectrum.cc:12-35) when the census never comes to the host: one histogram kernel over the
+    census energies per cycle; checked against the same census downloaded and binned with the reference's group search,
+    and against the all-CPU chain's spectrum file."""
+    deck_name, over, cycles = CASES["cts2_split"]
+    deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / "spectrum.inp"))
+    cpu = host.MonteCarlo(["-i", deck, "-e", str(tmp_path / "cpu")])
+    cpu.set_strict_math(True)
+    mc = host.MonteCarlo(["-i", deck, "-e", str(tmp_path / "gpu")])
+    dt = mc.get_double("dt")
+    ctx = device.DeviceContext(mc.image, dt, validation=True, particle_capacity=1 << 20)
+    edges = mc.image.array("energies").copy()
+    running = np.zeros(len(edges), dtype=np.uint64)
+    for _ in range(cycles):
+        cpu.cycle_init()
+        want = H.oracle_track(cpu.image, dt, cpu.processing(), strict=True, threads=1, want_flux=True)
+        cpu.set_tracking_result(want.census, want.balance, want.flux.sum())
+        cpu.cycle_finalize()
+        mc.cycle_init_resident(ctx)
+        mc.cycle_tracking_resident(ctx)
+        census = ctx.get_census()
+        hist = np.bincount(_reference_groups(edges, census["kinetic_energy"]), minlength=len(edges)).astype(np.uint64)
+        assert np.array_equal(ctx.census_energy_spectrum(), hist)
+        running += hist
+        mc.cycle_finalize()
+        assert np.array_equal(mc.energy_spectrum(), running)
+    assert int(running.sum()) > 0 and np.array_equal(mc.energy_spectrum(), cpu.energy_spectrum())
+    mc.write_energy_spectrum(), cpu.write_energy_spectrum()
+    assert (tmp_path / "gpu.dat").read_text() == (tmp_path / "cpu.dat").read_text()
+    # a streamed census (136-byte records in device memory) is binned through the same kernel with a record stride
+    mc.census_to_host(ctx)
+    mc.cycle_init()
+    mc.cycle_tracking(ctx)
+    census = mc.processed()
+    hist = np.bincount(_reference_groups(edges, census["kinetic_energy"]), minlength=len(edges)).astype(np.uint64)
+    assert np.array_equal(ctx.census_energy_spectrum(), hist)
+    ctx.close()
+    mc.close()
+    cpu.close()
