@@ -182,6 +182,21 @@ int  qsb_mc_cross_sections_text(qsb_mc* mc, char* buf, uint64_t cap, uint64_t* n
  * *passed (optional): number of tests that passed, out of 4. */
 int  qsb_mc_coral_benchmark_report(qsb_mc* mc, const double* fluence, uint64_t n_cells, char* buf, uint64_t cap, uint64_t* needed,
                                    int32_t* passed);
+/* The reference's timer table (MC_Fast_Timer, src/MC_Fast_Timer.{hh,cc}): seven named wall-clock sections in microseconds.
+ * The library times the qsb_mc_* calls that cover a whole section -- cycleInit (qsb_mc_cycle_init[_resident]), cycleTracking
+ * (qsb_mc_cycle_tracking[_resident], or qsb_mc_tracking_begin ... qsb_mc_tracking_end, or the end of
+ * qsb_mc_cycle_init_resident ... qsb_mc_tracking_end_resident), cycleTracking_Kernel (CUDA-event time of the launches),
+ * cycleFinalize, main (since qsb_mc_create) -- and the caller adds what it runs itself (a multi-rank driver's exchange:
+ * cycleTracking_MPI, cycleTracking_Test_Done) with qsb_mc_timer_add.
+ * qsb_mc_format_timer_report: last_cycle = 0 -> Cumulative_Report (src/MC_Fast_Timer.cc:58-105): heading, one line per timer
+ * (calls, min / avg / max / stddev over ranks, efficiency) and the Figure Of Merit line = segments / max over ranks of the
+ * cycleTracking time; last_cycle = 1 -> Last_Cycle_Report (:107-152, what `cycleTimers: 1` prints after every cycle).
+ * Every rank calls it (it reduces); the text is rank 0's. */
+enum { QSB_TIMER_MAIN = 0, QSB_TIMER_CYCLE_INIT, QSB_TIMER_CYCLE_TRACKING, QSB_TIMER_CYCLE_TRACKING_KERNEL, QSB_TIMER_CYCLE_TRACKING_MPI,
+       QSB_TIMER_CYCLE_TRACKING_TEST_DONE, QSB_TIMER_CYCLE_FINALIZE, QSB_TIMER_COUNT };
+int  qsb_mc_timer_add(qsb_mc* mc, int timer, double microseconds, uint64_t calls);
+int  qsb_mc_get_timer(qsb_mc* mc, int timer, double* cumulative_microseconds, uint64_t* calls);
+int  qsb_mc_format_timer_report(qsb_mc* mc, int last_cycle, char* buf, uint64_t cap, uint64_t* needed);
 /* the reference's closing line: Figure Of Merit = segments / cycle-tracking seconds (src/MC_Fast_Timer.cc:97-104) */
 int  qsb_mc_format_figure_of_merit(qsb_mc* mc, double tracking_seconds, char* buf, uint64_t cap);
 int  qsb_mc_format_cycle_row(qsb_mc* mc, int cycle, const uint64_t row[QSB_BAL_COUNT], double flux,

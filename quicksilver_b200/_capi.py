@@ -131,6 +131,9 @@ def _declare(lib):
                                                C.c_char_p, C.c_uint64]),
         "qsb_mc_coral_benchmark_report": (C.c_int, [vp, _P(C.c_double), C.c_uint64, C.c_char_p, C.c_uint64, u64p, _P(C.c_int32)]),
         "qsb_mc_format_figure_of_merit": (C.c_int, [vp, C.c_double, C.c_char_p, C.c_uint64]),
+        "qsb_mc_timer_add": (C.c_int, [vp, C.c_int, C.c_double, C.c_uint64]),
+        "qsb_mc_get_timer": (C.c_int, [vp, C.c_int, _P(C.c_double), u64p]),
+        "qsb_mc_format_timer_report": (C.c_int, [vp, C.c_int, C.c_char_p, C.c_uint64, u64p]),
         "qsb_mc_last_error": (C.c_char_p, [vp]),
         "qsb_create": (C.c_int, [C.c_int, _P(Image), C.c_double, _P(Options), _P(vp)]),
         "qsb_destroy": (C.c_int, [vp]),

@@ -64,6 +64,20 @@ struct Tallies
     bool spectrumDoneThisCycle = false;           // the resident path histograms the census on the device before finalize
 };
 
+// MC_Fast_Timer (src/MC_Fast_Timer.hh:27-58): the reference's seven named wall-clock sections, in microseconds.  The library
+// times the qsb_mc_* calls that cover a whole section itself; a caller that runs part of a section on its own (the exchange
+// rounds of a multi-rank driver) adds its share with qsb_mc_timer_add.
+struct FastTimers
+{
+    enum { Main = 0, CycleInit, CycleTracking, CycleTrackingKernel, CycleTrackingMPI, CycleTrackingTestDone, CycleFinalize, Count };
+    double   cumulativeClock[Count] = { 0 }, lastCycleClock[Count] = { 0 };
+    uint64_t numCalls[Count] = { 0 };
+    double   created = 0.0;            // steady-clock microseconds at construction: start of `main`
+    double   trackingStart = -1.0;     // start of the cycle's tracking section when it spans several calls
+    void add(int t, double microseconds, uint64_t calls) { cumulativeClock[t] += microseconds; lastCycleClock[t] += microseconds; numCalls[t] += calls; }
+    void clearLastCycle() { for (double& v : lastCycleClock) v = 0.0; }
+};
+
 class MonteCarlo
 {
 public:
@@ -76,6 +90,7 @@ public:
     DecompositionInfo ddc;
     std::vector<Domain> domain;
     Tallies           tallies;
+    FastTimers        timers;
     ParticleVault     processing, processed;
     double            timeStep;
     int               cycle = 0;

@@ -1,5 +1,6 @@
 // capi_host.cc -- extern "C" entry points of the host model (qsb_mc_*), see include/qsb.h.
 // Every entry point catches exceptions and reports through the return code + qsb_mc_last_error.
+#include <cmath>
 #include <cstdio>
 #include <chrono>
 #include <cstdlib>
@@ -24,6 +25,19 @@ struct qsb_mc
 
 namespace {
 thread_local std::string g_createError;
+
+double nowMicroseconds()
+{
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// times one section of the reference's timer table for the life of the object
+struct SectionTimer
+{
+    FastTimers& t; int which; double t0;
+    SectionTimer(FastTimers& timers, int w) : t(timers), which(w), t0(nowMicroseconds()) {}
+    ~SectionTimer() { t.add(which, nowMicroseconds() - t0, 1); }
+};
 
 template <typename F>
 int guarded(qsb_mc* h, F&& body)
@@ -50,6 +64,7 @@ int qsb_mc_create(int argc, const char* const* argv, int rank, int n_ranks, qsb_
     {
         Parameters params = getParameters(argc, argv);
         h->mc = new MonteCarlo(params, rank, n_ranks);
+        h->mc->timers.created = nowMicroseconds();            // MC_FASTTIMER_START(main) "once mcco exists" (src/main.cc:50)
     }
     catch (const std::exception& e)
     {
@@ -105,6 +120,7 @@ int qsb_mc_get_int(qsb_mc* h, const char* key, int64_t* out)
         else if (k == "nGroups") *out = s.nGroups;
         else if (k == "loadBalance") *out = s.loadBalance;
         else if (k == "coralBenchmark") *out = s.coralBenchmark;
+        else if (k == "cycleTimers") *out = s.cycleTimers;
         else if (k == "nBatches") *out = (int64_t)s.nBatches; else if (k == "batchSize") *out = (int64_t)s.batchSize;
         else if (k == "bTally") *out = s.balanceTallyReplications;
         else if (k == "fTally") *out = s.fluxTallyReplications;
@@ -149,6 +165,8 @@ int qsb_mc_cycle_init(qsb_mc* h)
                        "(or continue with qsb_mc_cycle_init_resident)";
             return (int)QSB_ERR_STATE;
         }
+        mc.timers.clearLastCycle();                           // Last_Cycle_Report clears them at the end of a cycle (src/MC_Fast_Timer.cc:151)
+        SectionTimer timer(mc.timers, FastTimers::CycleInit);
         cycleInit(mc);
         mc.sourcePlanId++;          // the host advanced the cells' source counts: a device copy of them is stale
         return (int)QSB_OK;
@@ -191,6 +209,7 @@ int qsb_mc_set_tracking_result(qsb_mc* h, const qsb_base_particle* census, uint6
 int qsb_mc_cycle_finalize(qsb_mc* h, uint64_t row[QSB_BAL_COUNT], double* flux)
 {
     return guarded(h, [&](MonteCarlo& mc) {
+        SectionTimer timer(mc.timers, FastTimers::CycleFinalize);
         Balance r; double f = 0;
         cycleFinalize(mc, r, f);
         if (row) std::memcpy(row, r.v, sizeof(r.v));
@@ -348,6 +367,72 @@ int qsb_mc_coral_benchmark_report(qsb_mc* h, const double* fluence, uint64_t n_c
     });
 }
 
+int qsb_mc_timer_add(qsb_mc* h, int timer, double microseconds, uint64_t calls)
+{
+    if (timer < 0 || timer >= FastTimers::Count) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) { mc.timers.add(timer, microseconds, calls); return QSB_OK; });
+}
+
+int qsb_mc_get_timer(qsb_mc* h, int timer, double* cumulative_microseconds, uint64_t* calls)
+{
+    if (timer < 0 || timer >= FastTimers::Count) return QSB_ERR_ARG;
+    return guarded(h, [&](MonteCarlo& mc) {
+        if (cumulative_microseconds) *cumulative_microseconds = mc.timers.cumulativeClock[timer];
+        if (calls) *calls = mc.timers.numCalls[timer];
+        return QSB_OK;
+    });
+}
+
+// MC_Fast_Timer_Container::Cumulative_Report / Last_Cycle_Report (src/MC_Fast_Timer.cc:58-152), the reference's wording and
+// column formats.  min / avg / max / stddev are over ranks (allreduce hook; single rank: all equal, stddev 0).
+int qsb_mc_format_timer_report(qsb_mc* h, int last_cycle, char* buf, uint64_t cap, uint64_t* needed)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        static const char* names[FastTimers::Count] = { "main", "cycleInit", "cycleTracking", "cycleTracking_Kernel", "cycleTracking_MPI",
+                                                        "cycleTracking_Test_Done", "cycleFinalize" };
+        FastTimers& t = mc.timers;
+        double clock[FastTimers::Count];
+        for (int i = 0; i < FastTimers::Count; ++i) clock[i] = std::floor(last_cycle ? t.lastCycleClock[i] : t.cumulativeClock[i]);   // the reference counts whole microseconds
+        uint64_t calls[FastTimers::Count];
+        for (int i = 0; i < FastTimers::Count; ++i) calls[i] = t.numCalls[i];
+        if (!last_cycle) { clock[FastTimers::Main] = std::floor(nowMicroseconds() - t.created); calls[FastTimers::Main] = 1; }  // MC_FASTTIMER_STOP(main)
+        double sum[FastTimers::Count], sumsq[FastTimers::Count], mx[FastTimers::Count], negmin[FastTimers::Count];
+        for (int i = 0; i < FastTimers::Count; ++i) { sum[i] = clock[i]; sumsq[i] = clock[i] * clock[i]; mx[i] = clock[i]; negmin[i] = -clock[i]; }
+        if (mc.allreduce && mc.nRanks > 1)
+        {
+            mc.allreduce(mc.allreduceUser, sum, FastTimers::Count, 0);
+            mc.allreduce(mc.allreduceUser, sumsq, FastTimers::Count, 0);
+            mc.allreduce(mc.allreduceUser, mx, FastTimers::Count, 2);
+            mc.allreduce(mc.allreduceUser, negmin, FastTimers::Count, 2);
+        }
+        std::string out;
+        char line[256];
+        const char* what = last_cycle ? "Last Cycle" : "Cumulative";
+        std::snprintf(line, sizeof line, "\n%-25s %12s %12s %12s %12s %12s %12s\n", "Timer", what, what, what, what, what, what); out += line;
+        std::snprintf(line, sizeof line, "%-25s %12s %12s %12s %12s %12s %12s\n", "Name", "number", "microSecs", "microSecs", "microSecs", "microSecs", "Efficiency"); out += line;
+        std::snprintf(line, sizeof line, "%-25s %12s %12s %12s %12s %12s %12s\n", "", "of calls", "min", "avg", "max", "stddev", "Rating"); out += line;
+        for (int i = 0; i < FastTimers::Count; ++i)
+        {
+            const double ave = std::floor(sum[i] / mc.nRanks);                       // integer average, as the reference's uint64 division
+            const double var = sumsq[i] / mc.nRanks - (sum[i] / mc.nRanks) * (sum[i] / mc.nRanks);
+            std::snprintf(line, sizeof line, "%-25s %12lu %12.3e %12.3e %12.3e %12.3e %12.2f\n", names[i], (unsigned long)calls[i], -negmin[i], ave, mx[i],
+                          std::sqrt(var > 0.0 ? var : 0.0), (100.0 * ave) / (mx[i] + 1.0e-80));
+            out += line;
+        }
+        if (!last_cycle)
+        {
+            const double segs = (double)mc.tallies.balanceCumulative[QSB_BAL_NUM_SEGMENTS];
+            std::snprintf(line, sizeof line, "%-25s %12.3e %-25s\n", "Figure Of Merit", segs / (mx[FastTimers::CycleTracking] * 1e-6),
+                          "[Num Segments / Cycle Tracking Time]");
+            out += line;
+        }
+        if (mc.rank != 0) out.clear();
+        if (needed) *needed = out.size() + 1;
+        if (buf && cap) std::snprintf(buf, cap, "%s", out.c_str());
+        return QSB_OK;
+    });
+}
+
 int qsb_mc_format_figure_of_merit(qsb_mc* h, double tracking_seconds, char* buf, uint64_t cap)
 {
     if (!buf || !cap) return QSB_ERR_ARG;
@@ -403,6 +488,7 @@ extern "C" int qsb_mc_tracking_begin(qsb_mc* h, qsb_ctx* ctx)
     return guarded(h, [&](MonteCarlo& mc) {
         auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
         int rc;
+        mc.timers.trackingStart = nowMicroseconds();
         if ((rc = qsb_cycle_begin(ctx, 0)) != QSB_OK) return fail(rc);
         // the census is delivered straight into the processed vault (page-locked, see MonteCarlo.hh); its size is not
         // known in advance: start from the input size plus headroom, any excess is fetched at the end
@@ -448,6 +534,8 @@ extern "C" int qsb_mc_tracking_end(qsb_mc* h, qsb_ctx* ctx)
                                        QSB_BAL_PRODUCE, QSB_BAL_SCATTER, QSB_BAL_NUM_SEGMENTS };
         for (int i : tracked) mc.tallies.balanceTask[i] += bal[i];
         mc.tallies.scalarFluxSum += flux;
+        if (mc.timers.trackingStart >= 0.0) mc.timers.add(FastTimers::CycleTracking, nowMicroseconds() - mc.timers.trackingStart, 1);
+        mc.timers.trackingStart = -1.0;
         return (int)QSB_OK;
     });
 }
@@ -467,6 +555,8 @@ extern "C" int qsb_mc_cycle_tracking(qsb_mc* h, qsb_ctx* ctx, qsb_track_stats* s
         return rc;
     }
     const double t2 = now();
+    if (h && h->mc) h->mc->timers.add(FastTimers::CycleTrackingKernel, 1e3 * (double)(stats ? stats->device_ms : local.device_ms),
+                                      (stats ? stats->n_launches : local.n_launches));
     rc = qsb_mc_tracking_end(h, ctx);
     if (trace)
         std::fprintf(stderr, "[qsb] cycle_tracking: begin %.2f ms, track %.2f ms (kernel %.2f ms), end %.2f ms\n", t1 - t0, t2 - t1,
@@ -486,6 +576,12 @@ extern "C" int qsb_mc_cycle_init_resident(qsb_mc* h, qsb_ctx* ctx, qsb_cycle_ini
     return guarded(h, [&](MonteCarlo& mc) {
         auto fail = [&](int rc) { h->error = std::string("device: ") + qsb_last_error(ctx); return rc; };
         int rc;
+        mc.timers.clearLastCycle();
+        struct InitSection            // cycleInit ends, and the tracking section begins, when this call returns
+        {
+            FastTimers& t; double t0;
+            ~InitSection() { const double t1 = nowMicroseconds(); t.add(FastTimers::CycleInit, t1 - t0, 1); t.trackingStart = t1; }
+        } section{ mc.timers, nowMicroseconds() };
         if (!mc.residentCensus)
         {
             // coming from host-side cycles (or the very first cycle): last cycle's census is the processed vault
@@ -589,6 +685,8 @@ extern "C" int qsb_mc_tracking_end_resident(qsb_mc* h, qsb_ctx* ctx)
         mc.tallies.scalarFluxSum += flux;
         mc.residentCensus = true;
         mc.residentCensusCount = nCensus;
+        if (mc.timers.trackingStart >= 0.0) mc.timers.add(FastTimers::CycleTracking, nowMicroseconds() - mc.timers.trackingStart, 1);
+        mc.timers.trackingStart = -1.0;
         return (int)QSB_OK;
     });
 }
@@ -603,6 +701,8 @@ extern "C" int qsb_mc_cycle_tracking_resident(qsb_mc* h, qsb_ctx* ctx, qsb_track
         h->error = std::string("device: ") + qsb_last_error(ctx);
         return rc;
     }
+    if (h->mc) h->mc->timers.add(FastTimers::CycleTrackingKernel, 1e3 * (double)(stats ? stats->device_ms : local.device_ms),
+                                 (stats ? stats->n_launches : local.n_launches));
     return qsb_mc_tracking_end_resident(h, ctx);
 }
 

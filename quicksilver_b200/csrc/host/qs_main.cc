@@ -52,6 +52,8 @@ int main(int argc, char** argv)
     const char* res_env = std::getenv("QSB_RESIDENT");
     const bool resident = res_env ? res_env[0] == '1' : opt.validation == 0;
 
+    int64_t cycle_timers = 0;
+    qsb_mc_get_int(mc, "cycleTimers", &cycle_timers);
     double t_track_total = 0;
     for (int cycle = 0; cycle < n_steps; ++cycle)
     {
@@ -70,19 +72,27 @@ int main(int argc, char** argv)
         qsb_mc_format_cycle_row(mc, cycle, row, flux, t1 - t0, t2 - t1, t3 - t2, line, sizeof line);
         std::printf("%s", line);
         t_track_total += t2 - t1;
+        if (cycle_timers)                                          // Last_Cycle_Report (src/main.cc:61-65)
+        {
+            char report[4096];
+            qsb_mc_format_timer_report(mc, 1, report, sizeof report, nullptr);
+            std::printf("%s", report);
+        }
     }
-    // coralBenchmarkCorrectness (src/main.cc:73, src/CoralBenchmark.cc) + figure of merit (src/MC_Fast_Timer.cc:97-104)
+    // gameOver (src/main.cc:87-94): timer table + figure of merit (src/MC_Fast_Timer.cc:58-105), spectrum file; then
+    // coralBenchmarkCorrectness (src/main.cc:73, src/CoralBenchmark.cc)
     {
+        char timers[4096];
+        qsb_mc_format_timer_report(mc, 0, timers, sizeof timers, nullptr);
+        std::printf("%s", timers);
+        qsb_mc_write_energy_spectrum(mc);
         std::vector<double> fluence((size_t)image.n_cells, 0.0);
         qsb_get_fluence(ctx, fluence.data());
         std::vector<char> report(8192);
         qsb_mc_coral_benchmark_report(mc, fluence.data(), fluence.size(), report.data(), report.size(), nullptr, nullptr);
         std::printf("%s", report.data());
-        qsb_mc_write_energy_spectrum(mc);          // src/main.cc:93 (nothing unless -e / energySpectrum names a file)
-        char fom[256];
-        qsb_mc_format_figure_of_merit(mc, t_track_total, fom, sizeof fom);
-        std::printf("%s", fom);
     }
+    (void)t_track_total;
     qsb_destroy(ctx);
     qsb_mc_destroy(mc);
     return 0;

@@ -245,11 +245,22 @@ class Simulation:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         view[:] = t.cpu().numpy()
 
-    def report(self, tracking_seconds):
-        """the reference's closing report (src/main.cc:66-80): CORAL self checks + figure of merit; text on rank 0."""
+    def report(self, tracking_seconds=None):
+        """the reference's closing report (src/main.cc:66-94): timer table + figure of merit (MC_Fast_Timer), spectrum file,
+        CORAL self checks; text on rank 0, every rank calls it (the reports reduce over ranks)."""
+        timers = self.mc.timer_report()
+        self.mc.write_energy_spectrum()
         fluence = self.ctx.get_fluence() if self.ctx is not None else None
         text, passed = self.mc.coral_benchmark_report(fluence)
-        return text + (self.mc.format_figure_of_merit(tracking_seconds) if self.rank == 0 else ""), passed
+        return timers + text, passed
+
+    def _feed_exchange_timers(self, t_track, rounds):
+        """several ranks: the tracking section is driven from here (exchange rounds), so its kernel / exchange split is ours
+        to report: cycleTracking_Kernel = CUDA-event time of the launches, cycleTracking_MPI = the rest of the section."""
+        kernel_us = 1e3 * getattr(self.backend, "device_ms", 0.0)
+        self.mc.timer_add("cycleTracking_Kernel", kernel_us, rounds)
+        self.mc.timer_add("cycleTracking_MPI", max(0.0, 1e6 * t_track - kernel_us), rounds)
+        self.mc.timer_add("cycleTracking_Test_Done", 0.0, rounds)
 
     def cycle(self):
         """one cycle; returns (global balance row, global flux sum, timings dict)."""
@@ -262,8 +273,10 @@ class Simulation:
                 stats = self.mc.cycle_tracking_resident(self.ctx)
                 info.update(device_ms=stats.device_ms, launches=stats.n_launches, rounds=1)
             else:
+                self.backend.device_ms = 0.0
                 rounds, sent = exchange_rounds(self.backend, self.dist, self.rank, self.world)
                 self.mc.tracking_end_resident(self.ctx)
+                self._feed_exchange_timers(time.perf_counter() - t1, rounds)
                 info.update(rounds=rounds, sent=sent)
             t2 = time.perf_counter()
             row, flux = self.mc.cycle_finalize()
@@ -276,9 +289,11 @@ class Simulation:
             stats = self.mc.cycle_tracking(self.ctx)
             info.update(device_ms=stats.device_ms, launches=stats.n_launches, rounds=1)
         elif hasattr(self.backend, "begin_streamed"):
+            self.backend.device_ms = 0.0
             self.backend.begin_streamed(self.mc)
             rounds, sent = exchange_rounds(self.backend, self.dist, self.rank, self.world)
             self.backend.end_streamed(self.mc)
+            self._feed_exchange_timers(time.perf_counter() - t1, rounds)
             info.update(rounds=rounds, sent=sent)
         else:
             vault = self.mc.processing()
@@ -286,6 +301,7 @@ class Simulation:
             rounds, sent = exchange_rounds(self.backend, self.dist, self.rank, self.world)
             census, balance, flux_sum = self.backend.results()
             self.mc.set_tracking_result(census, balance, flux_sum)
+            self.mc.timer_add("cycleTracking", 1e6 * (time.perf_counter() - t1), 1)
             info.update(rounds=rounds, sent=sent)
         t2 = time.perf_counter()
         row, flux = self.mc.cycle_finalize()

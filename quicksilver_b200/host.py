@@ -184,6 +184,25 @@ class MonteCarlo:
         self._check(self._lib.qsb_mc_coral_benchmark_report(self._h, ptr, n, buf, 8192, C.byref(need), C.byref(passed)))
         return buf.value.decode(), passed.value
 
+    TIMERS = ("main", "cycleInit", "cycleTracking", "cycleTracking_Kernel", "cycleTracking_MPI", "cycleTracking_Test_Done", "cycleFinalize")
+
+    def timer_add(self, name, microseconds, calls=1):
+        """add a caller-timed share to one of the reference's seven timers (MC_Fast_Timer)."""
+        self._check(self._lib.qsb_mc_timer_add(self._h, self.TIMERS.index(name), float(microseconds), int(calls)))
+
+    def timer(self, name):
+        """(cumulative microseconds, number of calls) of one timer on this rank."""
+        us, calls = C.c_double(), C.c_uint64()
+        self._check(self._lib.qsb_mc_get_timer(self._h, self.TIMERS.index(name), C.byref(us), C.byref(calls)))
+        return us.value, calls.value
+
+    def timer_report(self, last_cycle=False):
+        """Cumulative_Report (timer table + Figure Of Merit line) or Last_Cycle_Report; text on rank 0, every rank calls."""
+        need = C.c_uint64()
+        buf = C.create_string_buffer(4096)
+        self._check(self._lib.qsb_mc_format_timer_report(self._h, int(bool(last_cycle)), buf, 4096, C.byref(need)))
+        return buf.value.decode()
+
     def format_figure_of_merit(self, tracking_seconds):
         buf = C.create_string_buffer(256)
         self._check(self._lib.qsb_mc_format_figure_of_merit(self._h, float(tracking_seconds), buf, 256))

@@ -44,8 +44,10 @@ def main():
         census["cell"] = gid[census["cell"]]
         census["domain"] = 0
         np.save(os.path.join(out_dir, "census_c%d_r%d.npy" % (c, rank)), census)
+    report, passed = sim.report()            # collective: timer table (min/avg/max over ranks) + FOM + CORAL self checks
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as f:
-        json.dump({"rows": rows, "info": info, "exchange": getattr(sim, "exchange", "rounds")}, f)
+        json.dump({"rows": rows, "info": info, "exchange": getattr(sim, "exchange", "rounds"), "report": report,
+                   "tracking_us": sim.mc.timer("cycleTracking")[0]}, f)
     dist.barrier()
     dist.destroy_process_group()
 

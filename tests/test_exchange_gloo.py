@@ -72,3 +72,16 @@ def test_domain_decomposed_run_equals_single_rank_run(tmp_path, deck_name, grid,
         assert abs(got[13] - want[13]) <= 1e-11 * abs(want[13])
         union = np.concatenate([np.load(out / ("census_c%d_r%d.npy" % (c, r))) for r in range(world)])
         assert H.sort_particles(union).tobytes() == H.sort_particles(want_census[c]).tobytes(), "cycle %d census" % c
+    # the closing report is rank 0's; its timer table is reduced over the ranks (src/MC_Fast_Timer.cc:58-105)
+    assert all(ranks[r]["report"] == "" for r in range(1, world))
+    report = ranks[0]["report"]
+    line = [l for l in report.splitlines() if l.startswith("cycleTracking ")][0].split()
+    times = [ranks[r]["tracking_us"] for r in range(world)]
+    assert int(line[1]) == cycles
+    assert float(line[2]) == pytest.approx(min(times), rel=2e-3) and float(line[4]) == pytest.approx(max(times), rel=2e-3)
+    assert float(line[3]) == pytest.approx(sum(times) / world, rel=2e-3)
+    segs = sum(row[12] for row in ranks[0]["rows"])
+    fom = [l for l in report.splitlines() if l.startswith("Figure Of Merit")][0].split()
+    assert float(fom[3]) == pytest.approx(segs / (max(times) * 1e-6), rel=2e-3)
+    if deck_name == "Coral2_P1":
+        assert "Test for lost / unaccounted for particles in this simulation\nPASS:: No Particles Lost During Run" in report

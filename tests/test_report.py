@@ -67,3 +67,46 @@ def test_report_flags_broken_ratios_and_lost_particles(tmp_path):
     assert "FAIL:: Particles Were Lost During Run, test for done should have failed" in text
     assert "PASS:: Fluence is homogenous across cells with 6% tolerance" in text
     assert passed == 1
+
+
+def _skeleton(text):
+    """a report with every number replaced by '#': layout, names and wording only"""
+    import re
+    return re.sub(r" +", " ", re.sub(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", "#", text))      # (column widths: exact lines below)
+
+
+@pytest.mark.skipif(not os.path.exists(H.REF_QS), reason="oracle/_ref/qs not built (needs /root/reference)")
+def test_timer_report_has_the_reference_layout(tmp_path):
+    """Cumulative_Report / Last_Cycle_Report (src/MC_Fast_Timer.cc:58-152): same headings, timer names, column formats and
+    Figure Of Merit line as the reference binary prints (numbers differ: they are wall-clock times)."""
+    import subprocess
+    deck = decks.write_deck(decks.derive("CTS2_1", nx=4, ny=4, nz=4, lx=4, ly=4, lz=4, nParticles=640, nSteps=2, cycleTimers=1), str(tmp_path / "t.inp"))
+    out = subprocess.run([H.REF_QS, "-i", deck], check=True, stdout=subprocess.PIPE, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")).stdout
+    import re
+    ref_cumulative = out[re.search(r"\nTimer +Cumulative", out).start():]
+    ref_cumulative = ref_cumulative[:ref_cumulative.index("[Num Segments / Cycle Tracking Time]") + len("[Num Segments / Cycle Tracking Time]") + 1]
+    first = re.search(r"\nTimer +Last Cycle", out).start()
+    ref_last = out[first:out.index("\n", out.index("cycleFinalize", first)) + 1]
+
+    mc = host.MonteCarlo(["-i", deck])
+    assert mc.get_int("cycleTimers") == 1
+    dt = mc.get_double("dt")
+    last_reports = []
+    for _ in range(2):
+        mc.cycle_init()
+        r = H.oracle_track(mc.image, dt, mc.processing(), strict=False, threads=1)
+        mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+        mc.timer_add("cycleTracking", 1234.0, 1)                 # the tracking section belongs to the caller here
+        mc.timer_add("cycleTracking_Kernel", 1000.0, 3)
+        mc.cycle_finalize()
+        last_reports.append(mc.timer_report(last_cycle=True))
+    ours = mc.timer_report()
+    assert _skeleton(ours) == _skeleton(ref_cumulative), "\n--- got ---\n%s\n--- reference ---\n%s" % (ours, ref_cumulative)
+    assert _skeleton(last_reports[0]) == _skeleton(ref_last)
+    # the numbers: calls counted, last-cycle clocks cleared every cycle, FOM = segments / cycleTracking time
+    us, calls = mc.timer("cycleTracking")
+    assert (us, calls) == (2468.0, 2) and mc.timer("cycleInit")[1] == 2 and mc.timer("cycleFinalize")[1] == 2
+    assert "cycleTracking                        2    2.468e+03    2.468e+03    2.468e+03    0.000e+00       100.00" in ours
+    assert "cycleTracking                        2    1.234e+03" in last_reports[1]
+    segs = float(mc.cumulative_balance()[host.BAL["num_segments"]])
+    assert ours.endswith("%-25s %12.3e %-25s\n" % ("Figure Of Merit", segs / 2468e-6, "[Num Segments / Cycle Tracking Time]"))
