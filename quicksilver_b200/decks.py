@@ -119,6 +119,18 @@ def _no_fission():   # Examples/NoFission/noFission.inp
             "CrossSection": [_xs("flat", nuBar=2.4)]}
 
 
+def _no_collisions():   # Examples/NoCollisions/no.collisions.inp: total cross section 1e-80, particles only stream
+    sim = {"dt": 1e-08, "fMax": 0.1, "loadBalance": 1, "lx": 100, "ly": 100, "lz": 100, "nParticles": 1000000, "nSteps": 10,
+           "nx": 10, "ny": 10, "nz": 10, "seed": 1029384756, "xDom": 0, "yDom": 0, "zDom": 0, "eMax": 1.000001, "eMin": 1.000000,
+           "nGroups": 230}
+    mats = [_material("boxMaterial", nIsotopes=10, nReactions=9, sourceRate=0, totalCrossSection=1e-80,
+                      absorptionCrossSectionRatio=1, fissionCrossSectionRatio=0, scatteringCrossSectionRatio=1),
+            _material("sourceMaterial", nIsotopes=10, nReactions=9, sourceRate=1e10, totalCrossSection=1e-80,
+                      absorptionCrossSectionRatio=1, fissionCrossSectionRatio=1, scatteringCrossSectionRatio=1)]
+    return {"Simulation": sim, "Geometry": [_brick("boxMaterial", 100), _brick("sourceMaterial", 10)], "Material": mats,
+            "CrossSection": [_xs("flat", nuBar=2.4)]}
+
+
 DECKS = {
     "AllAbsorb": _limit_case(None, 1e10, (1, 0, 0)),
     "AllEscape": _limit_case("escape", 1e-20, (0, 0, 1)),
@@ -132,6 +144,7 @@ DECKS = {
     "Homogeneous_v7": _homogeneous(1e-06, 0.1, (0.1086, 0.0969, 0.7946), mass=12.011),
     "NonFlatXC": _nonflat(),
     "NoFission": _no_fission(),
+    "NoCollisions": _no_collisions(),
 }
 # scattering-only variant of NoFission (Examples/AllScattering/scatteringOnly.inp)
 DECKS["AllScattering"] = copy.deepcopy(DECKS["NoFission"])

@@ -40,6 +40,8 @@ CASES = {
     "nofission_octant": ("NoFission", dict(nx=5, ny=5, nz=5, lx=50, ly=50, lz=50, nParticles=2000, nSteps=3), 3, 2),
     "scattering_octant": ("AllScattering", dict(nx=5, ny=5, nz=5, lx=50, ly=50, lz=50, nParticles=2000, nSteps=2), 2, 1),
     "nonflat_two_materials": ("NonFlatXC", dict(nx=5, ny=5, nz=5, lx=50, ly=50, lz=50, nParticles=1500, nSteps=3, dt=5e-10), 3, 2),
+    # total cross section 1e-80: no collision ever, particles stream and reflect until census (Examples/NoCollisions)
+    "nocollisions_voronoi": ("NoCollisions", dict(nx=5, ny=5, nz=5, lx=50, ly=50, lz=50, nParticles=2000, nSteps=3), 3, 2),
     "homogeneous_v7": ("Homogeneous_v7", dict(nx=5, ny=5, nz=5, lx=100, ly=100, lz=100, xDom=1, yDom=1, zDom=1,
                                               nParticles=1250, nSteps=2), 2, 1),
 }

@@ -175,6 +175,19 @@ def test_known_answer_structure_of_limit_decks(tmp_path):
             assert b["collision"] == 0 and b["absorb"] == 0
 
 
+def test_no_collisions_deck_only_streams(tmp_path):
+    """Examples/NoCollisions (total cross section 1e-80, reflecting box): no collision ever happens, every particle is
+    followed facet by facet -- reflections included -- until census; the segment count is facet crossings + census."""
+    mc = _model("nocollisions_voronoi", tmp_path)
+    mc.cycle_init()
+    vault = mc.processing()
+    r = H.oracle_track(mc.image, mc.get_double("dt"), vault, strict=False, threads=1)
+    b = {k: int(r.balance[BAL[k]]) for k in BAL}
+    assert b["collision"] == b["absorb"] == b["scatter"] == b["fission"] == b["produce"] == b["escape"] == 0
+    assert b["census"] == len(vault) == len(r.census) and b["num_segments"] > b["census"]      # facet crossings = segments - census
+    assert r.n_forced_collisions == 0 and r.n_retry_moves == 0
+
+
 def test_strict_math_build_of_the_oracle_tracks_the_libm_build(tmp_path):
     """The device validation kernels use the portable log/sin/cos of csrc/qs_strict_math.h so that CPU and GPU
     agree bit for bit; that variant of the oracle must stay statistically indistinguishable from the libm one
