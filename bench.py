@@ -186,6 +186,7 @@ def main():
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
             t = json.load(f).get(args.workload)
         result["traffic"] = t["dram_bytes_per_launch"] if (t and args.scale == 1.0) else None
+        result["issue_bound_evidence"] = t.get("issue_bound_evidence") if t else None
     except Exception:
         result["traffic"] = None
     kernel_s = result["kernel_seconds_max"]
@@ -212,6 +213,9 @@ def main():
             "tracking_ms_per_step_rank0": result["tracking_ms_per_step_rank0"],
             "whole_cycle": result.get("whole_cycle"),
             "balance_check": result["balance_check"]}
+    if result.get("issue_bound_evidence"):
+        # the kernel is issue / latency bound, not HBM bound: the ncu numbers that say so, from the committed digest
+        line["roofline"]["issue_bound_evidence"] = result["issue_bound_evidence"]
     if line["roofline"]["dram_achieved"]:
         line["roofline"]["dram_frac"] = line["roofline"]["dram_achieved"] / peak
     wc = result.get("whole_cycle") or {}
