@@ -14,6 +14,10 @@
 #include <cstdlib>
 #include <mutex>
 #include <unordered_set>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace qsb {
 
@@ -214,39 +218,103 @@ void cycleInit(MonteCarlo& mc)
 
 namespace {
 
+// Host threads for the cycleInit stages (OpenMP).  Every particle decides from its own stream and lands in a slot fixed by
+// prefix sums, so the vault comes out in the same order -- the serial order -- whatever the thread count.
+int hostThreads()
+{
+    static const int n = [] {
+        if (const char* e = std::getenv("QSB_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) return v; }
+#ifdef _OPENMP
+        return omp_get_max_threads();
+#else
+        return 1;
+#endif
+    }();
+    return n;
+}
+constexpr size_t kParallelThreshold = 1u << 15;        // below this the serial loops are faster than waking a team
+
+template <class M>
+void fillSourceParticle(const MonteCarlo& mc, const Domain& d, size_t di, int c, uint64_t stream, double weight, qsb_base_particle& p)
+{
+    const SimulationParameters& sp = mc.params.simulationParams;
+    qs_source_particle sp1;
+    qs_source_one<M>(stream, &d.nodes[(size_t)c * 42], d.volume[c], sp.eMin, sp.eMax, mc.timeStep, &sp1);
+    std::memset(&p, 0, sizeof(p));
+    p.random_number_seed = sp1.random_number_seed;
+    p.identifier = sp1.identifier;
+    for (int k = 0; k < 3; ++k) { p.coordinate[k] = sp1.coordinate[k]; p.velocity[k] = sp1.velocity[k]; }
+    p.kinetic_energy = sp1.kinetic_energy;
+    p.domain = (int32_t)di; p.cell = c;
+    p.weight = weight;
+    p.num_mean_free_paths = sp1.num_mean_free_paths;
+    p.time_to_census = sp1.time_to_census;
+    p.last_event = QSB_EV_CENSUS;        // MC_Particle's default (src/MC_Base_Particle.hh:259)
+    p.species = 0;
+}
+
 template <class M>
 void sourceCells(MonteCarlo& mc, double weight)
 {
-    const SimulationParameters& sp = mc.params.simulationParams;
     const double dt = mc.timeStep;
+    // per-cell counts (src/MC_SourceNow.cc:72-76) and where each cell's particles go in the vault
+    struct CellRef { int domain, cell, n; size_t first; };
+    std::vector<CellRef> cells;
+    size_t total = 0;
     for (size_t di = 0; di < mc.domain.size(); ++di)
     {
-        Domain& d = mc.domain[di];
+        const Domain& d = mc.domain[di];
         for (int c = 0; c < d.nCells; ++c)
         {
             const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * dt;
             const int n = (int)(cellWeight / weight);
-            for (int i = 0; i < n; ++i)
-            {
-                qs_source_particle sp1;
-                qs_source_one<M>(d.sourceTally[c]++ + d.cellId[c], &d.nodes[(size_t)c * 42], d.volume[c], sp.eMin, sp.eMax, dt, &sp1);
-                qsb_base_particle p;
-                std::memset(&p, 0, sizeof(p));
-                p.random_number_seed = sp1.random_number_seed;
-                p.identifier = sp1.identifier;
-                for (int k = 0; k < 3; ++k) { p.coordinate[k] = sp1.coordinate[k]; p.velocity[k] = sp1.velocity[k]; }
-                p.kinetic_energy = sp1.kinetic_energy;
-                p.domain = (int32_t)di; p.cell = c;
-                p.weight = weight;
-                p.num_mean_free_paths = sp1.num_mean_free_paths;
-                p.time_to_census = sp1.time_to_census;
-                p.last_event = QSB_EV_CENSUS;        // MC_Particle's default (src/MC_Base_Particle.hh:259)
-                p.species = 0;
-                mc.processing.push_back(p);
-                mc.tallies.balanceTask[QSB_BAL_SOURCE]++;
-            }
+            if (n > 0) { cells.push_back(CellRef{ (int)di, c, n, total }); total += (size_t)n; }
         }
     }
+    const size_t base = mc.processing.size();
+    mc.processing.resize(base + total);
+    qsb_base_particle* out = mc.processing.data() + base;
+    const long nRef = (long)cells.size();
+#pragma omp parallel for schedule(static) num_threads(hostThreads()) if (total >= kParallelThreshold)
+    for (long r = 0; r < nRef; ++r)
+    {
+        const CellRef& ref = cells[r];
+        const Domain& d = mc.domain[ref.domain];
+        const uint64_t stream0 = d.sourceTally[ref.cell] + d.cellId[ref.cell];
+        for (int i = 0; i < ref.n; ++i)
+            fillSourceParticle<M>(mc, d, (size_t)ref.domain, ref.cell, stream0 + (uint64_t)i, weight, out[ref.first + i]);
+    }
+    for (const CellRef& ref : cells) mc.domain[ref.domain].sourceTally[ref.cell] += (uint64_t)ref.n;
+    mc.tallies.balanceTask[QSB_BAL_SOURCE] += total;
+}
+
+// keep[i] != 0 survivors of `v`, in order, become the vault; the old buffer is kept as scratch for the next time
+void compactKept(MonteCarlo& mc, const std::vector<uint8_t>& keep, size_t nKept)
+{
+    ParticleVault& v = mc.processing;
+    const size_t n = v.size();
+    ParticleVault& out = mc.scratch;
+    out.resize(nKept);
+    const int T = std::max(1, std::min<int>(hostThreads(), (int)(n / 4096) + 1));
+    std::vector<size_t> first(T + 1, 0);
+    const size_t chunk = (n + T - 1) / T;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t)
+    {
+        size_t k = 0;
+        for (size_t i = t * chunk, e = std::min(n, (t + 1) * chunk); i < e; ++i) k += keep[i] != 0;
+        first[t + 1] = k;
+    }
+    for (int t = 0; t < T; ++t) first[t + 1] += first[t];
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; ++t)
+    {
+        size_t dst = first[t];
+        for (size_t i = t * chunk, e = std::min(n, (t + 1) * chunk); i < e; ++i)
+            if (keep[i]) out[dst++] = v[i];
+    }
+    v.swap(out);
+    out.clear();
 }
 
 } // namespace
@@ -308,34 +376,55 @@ void populationControl(MonteCarlo& mc)
     if (factor == 1.0) return;
 
     // Every particle decides from its own stream, so the result does not depend on vault order; the
-    // reference walks the vault backwards and swap-erases, here survivors are compacted in place and
-    // split copies are appended behind the original population.
+    // reference walks the vault backwards and swap-erases, here survivors keep their order and
+    // split copies are appended behind the original population, parent by parent.
     ParticleVault& v = mc.processing;
     Balance& bal = mc.tallies.balanceTask;
-    size_t keep = 0;
-    for (size_t i = 0; i < localCount; ++i)
+    const long n = (long)localCount;
+    const bool parallel = localCount >= kParallelThreshold;
+    if (factor < 1)
     {
-        qsb_base_particle p = v[i];                     // by value: push_back below may reallocate
-        const int copies = qs_population_control_one(factor, &p.random_number_seed, &p.weight);
-        if (factor < 1)
+        std::vector<uint8_t> keep(localCount);
+        size_t kept = 0;
+#pragma omp parallel for schedule(static) reduction(+:kept) num_threads(hostThreads()) if (parallel)
+        for (long i = 0; i < n; ++i)
         {
-            if (copies < 0) { bal[QSB_BAL_RR]++; continue; }
-            v[keep++] = p;
+            qsb_base_particle& p = v[i];
+            keep[i] = qs_population_control_one(factor, &p.random_number_seed, &p.weight) >= 0;
+            kept += keep[i];
         }
-        else
+        bal[QSB_BAL_RR] += localCount - kept;
+        if (kept != localCount) compactKept(mc, keep, kept);
+    }
+    else
+    {
+        std::vector<int32_t> copies(localCount);
+#pragma omp parallel for schedule(static) num_threads(hostThreads()) if (parallel)
+        for (long i = 0; i < n; ++i)
         {
+            qsb_base_particle& p = v[i];
+            copies[i] = qs_population_control_one(factor, &p.random_number_seed, &p.weight);
+        }
+        std::vector<size_t> first(localCount + 1, 0);
+        for (size_t i = 0; i < localCount; ++i) first[i + 1] = first[i] + (size_t)copies[i];
+        const size_t nChildren = first[localCount];
+        v.resize(localCount + nChildren);                  // (may move the vault: take the pointer afterwards)
+        qsb_base_particle* rec = v.data();
+#pragma omp parallel for schedule(dynamic, 4096) num_threads(hostThreads()) if (parallel)
+        for (long i = 0; i < n; ++i)
+        {
+            if (copies[i] <= 0) continue;
+            qsb_base_particle& p = rec[i];
             qsb_base_particle child = p;
-            for (int k = 0; k < copies; ++k)
+            for (int k = 0; k < copies[i]; ++k)
             {
-                bal[QSB_BAL_SPLIT]++;
                 child.random_number_seed = qs_rng_spawn(&p.random_number_seed);
                 child.identifier = child.random_number_seed;
-                v.push_back(child);
+                rec[localCount + first[i] + k] = child;
             }
-            v[i] = p;
         }
+        bal[QSB_BAL_SPLIT] += nChildren;
     }
-    if (factor < 1) v.resize(keep);
 }
 
 void rouletteLowWeightParticles(MonteCarlo& mc)
@@ -344,16 +433,18 @@ void rouletteLowWeightParticles(MonteCarlo& mc)
     if (!(cutoff > 0.0)) return;
     const double weightCutoff = cutoff * mc.sourceParticleWeight;
     ParticleVault& v = mc.processing;
-    size_t keep = 0;
-    for (size_t i = 0; i < v.size(); ++i)
+    const long n = (long)v.size();
+    std::vector<uint8_t> keep(v.size());
+    size_t kept = 0;
+#pragma omp parallel for schedule(static) reduction(+:kept) num_threads(hostThreads()) if (v.size() >= kParallelThreshold)
+    for (long i = 0; i < n; ++i)
     {
         qsb_base_particle& p = v[i];
-        if (!qs_roulette_low_weight_one(cutoff, weightCutoff, &p.random_number_seed, &p.weight))
-        { mc.tallies.balanceTask[QSB_BAL_RR]++; continue; }
-        if (keep != i) v[keep] = p;
-        ++keep;
+        keep[i] = qs_roulette_low_weight_one(cutoff, weightCutoff, &p.random_number_seed, &p.weight) != 0;
+        kept += keep[i];
     }
-    v.resize(keep);
+    mc.tallies.balanceTask[QSB_BAL_RR] += v.size() - kept;
+    if (kept != v.size()) compactKept(mc, keep, kept);
 }
 
 void cycleFinalize(MonteCarlo& mc, Balance& row, double& flux)

@@ -92,6 +92,7 @@ public:
     Tallies           tallies;
     FastTimers        timers;
     ParticleVault     processing, processed;
+    ParticleVault     scratch;          // destination of cycleInit's compactions; swapped with `processing`, buffer kept
     double            timeStep;
     int               cycle = 0;
     double            sourceParticleWeight = 0.0;

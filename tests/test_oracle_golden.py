@@ -18,7 +18,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from quicksilver_b200 import host
+from quicksilver_b200 import decks, host
 from quicksilver_b200._capi import BAL, PARTICLE_DTYPE
 
 sys.path.insert(0, H.GOLDEN)
@@ -237,3 +237,63 @@ FACET_POINTS = [[1, 3, 8], [3, 7, 8], [7, 5, 8], [5, 1, 8], [0, 4, 9], [4, 6, 9]
                 [3, 2, 10], [2, 6, 10], [6, 7, 10], [7, 3, 10], [0, 1, 11], [1, 5, 11], [5, 4, 11], [4, 0, 11],
                 [4, 5, 12], [5, 7, 12], [7, 6, 12], [6, 4, 12], [0, 2, 13], [2, 3, 13], [3, 1, 13], [1, 0, 13]]
 OPPOSING_FACET = [7, 6, 5, 4, 3, 2, 1, 0, 12, 15, 14, 13, 8, 11, 10, 9, 20, 23, 22, 21, 16, 19, 18, 17]
+
+
+@pytest.mark.skipif(not os.path.exists(H.REF_DUMP), reason="oracle/_ref/qs_dump not built (needs /root/reference)")
+@pytest.mark.parametrize("deck_name,over", [
+    ("CTS2_1", dict(nSteps=3)),                                                       # 40 960 particles: source x10 split, then splits x ~4
+    ("Coral2_P1_1", dict(nSteps=3, nParticles=81920, nx=12, ny=12, nz=12, lx=12, ly=12, lz=12)),   # roulette (factor < 1) from cycle 1 on
+])
+def test_threaded_cycle_init_equals_the_reference_at_sizes_above_the_team_threshold(tmp_path, deck_name, over):
+    """the host cycleInit runs on an OpenMP team above 32 768 particles; the committed fixtures are smaller, so this one
+    dumps the reference's vaults live (oracle/_ref/qs_dump) and compares cycle by cycle"""
+    deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / "deck.inp"))
+    H.run_reference_dump(["-i", deck], str(tmp_path / "dump"), particle_cycles=3, threads=4)
+    mc = host.MonteCarlo(["-i", deck])
+    dt = mc.get_double("dt")
+    exercised = dict(rr=0, split=0)
+    for c in range(3):
+        ref = H.read_qsd(str(tmp_path / "dump" / ("cycle_%03d.qsd" % c)))
+        mc.cycle_init()
+        vault = mc.processing()
+        assert len(vault) > 32768
+        want = H.particles_from_bytes(ref["tracking_input"])
+        assert H.sort_particles(vault).tobytes() == H.sort_particles(want).tobytes(), "cycle %d processing vault" % c
+        r = H.oracle_track(mc.image, dt, vault, strict=False, threads=os.cpu_count() or 1)
+        mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+        row, _ = mc.cycle_finalize()
+        assert np.array_equal(row, ref["balance"]), "cycle %d balance row" % c
+        exercised["rr"] += int(row[BAL["rr"]]); exercised["split"] += int(row[BAL["split"]])
+    assert exercised["split"] > 0 if deck_name == "CTS2_1" else exercised["rr"] > 0
+
+
+_THREAD_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from quicksilver_b200 import decks, host
+mc = host.MonteCarlo(["-i", sys.argv[2]])
+h = hashlib.sha256()
+for cycle in range(4):
+    mc.cycle_init()
+    v = mc.processing()
+    h.update(v.tobytes())                      # NOT sorted: the vault order itself must not depend on the team size
+    # stand-in for tracking: cycle 1 keeps a third (forces splitting), cycle 2 triples the census (forces roulette)
+    census = v[::3] if cycle == 1 else (np.concatenate([v, v, v]) if cycle == 2 else v)
+    mc.set_tracking_result(census, np.zeros(13, np.uint64), 0.0)
+    row, _ = mc.cycle_finalize()
+    h.update(row.tobytes())
+print(h.hexdigest())
+"""
+
+
+def test_cycle_init_vault_is_identical_for_any_team_size(tmp_path):
+    import subprocess
+    import sys
+    deck = decks.write_deck(decks.derive("CTS2_1", nSteps=4, lowWeightCutoff=0.6), str(tmp_path / "deck.inp"))
+    digests = set()
+    for threads in ("1", "3", "8"):
+        out = subprocess.run([sys.executable, "-c", _THREAD_SCRIPT, H.ROOT, deck], check=True, stdout=subprocess.PIPE, text=True,
+                             env=dict(os.environ, QSB_HOST_THREADS=threads), timeout=600).stdout.strip()
+        digests.add(out)
+    assert len(digests) == 1, digests
