@@ -1,6 +1,7 @@
 // MonteCarlo.cc -- see MonteCarlo.hh.
 #include "MonteCarlo.hh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -225,7 +226,7 @@ int hostThreads()
     static const int n = [] {
         if (const char* e = std::getenv("QSB_HOST_THREADS")) { const int v = std::atoi(e); if (v > 0) return v; }
 #ifdef _OPENMP
-        return omp_get_max_threads();
+        return std::min(omp_get_max_threads(), 32);        // memory-bound loops: more threads than that buy nothing
 #else
         return 1;
 #endif
