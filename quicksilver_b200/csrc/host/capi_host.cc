@@ -622,16 +622,18 @@ extern "C" int qsb_mc_cycle_init_resident(qsb_mc* h, qsb_ctx* ctx, qsb_cycle_ini
         std::memset(&a, 0, sizeof a);
         a.plan_id = mc.sourcePlanId;
         a.source_offsets = mc.sourceOffsets.data();
-        // the device keeps and advances its own copy of the running source counts; it re-reads ours when the plan id moved
-        if (mc.devicePlanId != mc.sourcePlanId || mc.devicePlanCtx != (const void*)ctx)
+        // The device keeps and advances its own copy of the running source counts and re-reads ours when the plan id moves
+        // (or when the context has no plan yet: a context created at a destroyed one's address must not look familiar, so
+        // the arrays are handed over every time -- 8 bytes per cell -- and only the id says whether they are news).
+        mc.sourceTallyFlat.resize(nCells);
         {
-            mc.sourceTallyFlat.resize(nCells);
             size_t flat = 0;
             for (const Domain& d : mc.domain)
                 for (int c = 0; c < d.nCells; ++c, ++flat) mc.sourceTallyFlat[flat] = d.sourceTally[c];
-            a.source_tally = mc.sourceTallyFlat.data();
-            a.plan_id = ++mc.sourcePlanId;                 // a fresh id: this context has never seen it
         }
+        a.source_tally = mc.sourceTallyFlat.data();
+        if (mc.devicePlanId != mc.sourcePlanId || mc.devicePlanCtx != (const void*)ctx)
+            a.plan_id = ++mc.sourcePlanId;                 // a fresh id: this context has never seen it
         a.source_weight = weight;
         a.e_min = mc.params.simulationParams.eMin; a.e_max = mc.params.simulationParams.eMax;
         a.split_factor = populationControlFactor(mc, mc.residentCensusCount + nSource);
