@@ -359,6 +359,12 @@ int  qsb_mc_tracking_end(qsb_mc* mc, qsb_ctx* ctx);
  *                                   output, or to continue with host-side cycles).
  * Host and device cycles can be mixed freely; only host memory <-> device copies of the whole vault separate them. */
 int  qsb_mc_cycle_init_resident(qsb_mc* mc, qsb_ctx* ctx, qsb_cycle_init_result* result /* optional */);
+/* The global numbers of the coming cycle's cycleInit, as qsb_mc_cycle_init_resident hands them to the device, without
+ * side effects: source_offsets[n_cells+1], source_tally[n_cells] (either may be NULL), the weight of a source particle and
+ * the split / roulette factor for a rank whose carried-over census holds n_census particles (reduces over ranks when the
+ * deck says loadBalance 0: then every rank calls it). */
+int  qsb_mc_source_plan(qsb_mc* mc, int32_t* source_offsets, uint64_t* source_tally, double* source_weight, double* split_factor,
+                        uint64_t n_census);
 int  qsb_mc_cycle_tracking_resident(qsb_mc* mc, qsb_ctx* ctx, qsb_track_stats* stats /* optional */);
 int  qsb_mc_tracking_end_resident(qsb_mc* mc, qsb_ctx* ctx);
 int  qsb_mc_census_to_host(qsb_mc* mc, qsb_ctx* ctx);

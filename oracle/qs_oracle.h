@@ -41,6 +41,25 @@ int qso_track(const qsb_image* image, double time_step, int strict_math, int n_t
 
 int qso_energy_group(const qsb_image* image, double energy);
 
+/* cycleInit (src/main.cc:96-121), the step in front of the path, restated stage by stage in the reference's own order:
+ * last cycle's census becomes the vault, MC_SourceNow appends this cycle's source particles (src/MC_SourceNow.cc:74-126),
+ * PopulationControlGuts marches backwards over the vault, erase-swapping the killed and appending split copies
+ * (src/PopulationControl.cc:66-122), RouletteLowWeightParticles does the same for low weights (:127-171).
+ * The caller supplies the numbers that need the deck or other ranks: the per-cell source counts as a prefix sum
+ * (src/MC_SourceNow.cc:72-76), the cells' running source counts, the source particle weight (:59-61) and the split factor
+ * (src/PopulationControl.cc:32-57; 1.0 = stage skipped, :60).  Returns 0, or -1 if `out` is too small. */
+typedef struct qso_cycle_init_io {
+    /* in */
+    const qsb_base_particle* census;  uint64_t n_census;
+    const int32_t*  source_offsets;       /* [n_cells+1] */
+    const uint64_t* source_tally;         /* [n_cells]   */
+    double source_weight, e_min, e_max, time_step, split_factor, low_weight_cutoff;
+    /* out (caller allocated) */
+    qsb_base_particle* out;  uint64_t out_cap;  uint64_t n_out;
+    uint64_t n_source, n_rr, n_split;
+} qso_cycle_init_io;
+int qso_cycle_init(const qsb_image* image, int strict_math, qso_cycle_init_io* io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -120,6 +120,7 @@ def _declare(lib):
         "qsb_mc_cycle_tracking_resident": (C.c_int, [vp, vp, _P(TrackStats)]),
         "qsb_mc_tracking_end_resident": (C.c_int, [vp, vp]),
         "qsb_mc_census_to_host": (C.c_int, [vp, vp]),
+        "qsb_mc_source_plan": (C.c_int, [vp, _P(C.c_int32), u64p, _P(C.c_double), _P(C.c_double), C.c_uint64]),
         "qsb_cycle_init_resident": (C.c_int, [vp, _P(CycleInitArgs), _P(CycleInitResult)]),
         "qsb_put_census": (C.c_int, [vp, vp, C.c_uint64]),
         "qsb_mc_processing": (C.c_int, [vp, _P(vp), u64p]),

@@ -31,6 +31,33 @@ double nowMicroseconds()
     return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// The source plan of a cycle: weight of one source particle (src/MC_SourceNow.cc:41-61) and the per-cell counts
+// (int)(cellWeight / weight) (:72-76) as a prefix sum over flat cells.  Both are functions of the deck and the time step
+// only, so they are evaluated once (the weight walks every cell of every rank) and rebuilt when the time step changes.
+double buildSourcePlan(MonteCarlo& mc)
+{
+    if (mc.cachedSourceWeightDt != mc.timeStep) { mc.cachedSourceWeight = sourceParticleWeight(mc); mc.cachedSourceWeightDt = mc.timeStep; }
+    const double weight = mc.cachedSourceWeight;
+    const size_t nCells = (size_t)mc.image.n_cells;
+    if (mc.sourceOffsets.size() != nCells + 1 || weight != mc.sourcePlanWeight)
+    {
+        mc.sourceOffsets.assign(nCells + 1, 0);
+        size_t flat = 0;
+        for (const Domain& d : mc.domain)
+            for (int c = 0; c < d.nCells; ++c, ++flat)
+            {
+                const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * mc.timeStep;
+                const int n = (int)(cellWeight / weight);
+                const int64_t next = (int64_t)mc.sourceOffsets[flat] + (n > 0 ? n : 0);
+                if (next > INT32_MAX) throw std::runtime_error("more than 2^31 source particles on one rank");
+                mc.sourceOffsets[flat + 1] = (int32_t)next;
+            }
+        mc.sourcePlanWeight = weight;
+        mc.sourcePlanId++;
+    }
+    return weight;
+}
+
 // times one section of the reference's timer table for the life of the object
 struct SectionTimer
 {
@@ -170,6 +197,25 @@ int qsb_mc_cycle_init(qsb_mc* h)
         cycleInit(mc);
         mc.sourcePlanId++;          // the host advanced the cells' source counts: a device copy of them is stale
         return (int)QSB_OK;
+    });
+}
+
+int qsb_mc_source_plan(qsb_mc* h, int32_t* source_offsets, uint64_t* source_tally, double* source_weight, double* split_factor,
+                       uint64_t n_census)
+{
+    return guarded(h, [&](MonteCarlo& mc) {
+        const double weight = buildSourcePlan(mc);
+        const size_t nCells = (size_t)mc.image.n_cells;
+        if (source_offsets) std::memcpy(source_offsets, mc.sourceOffsets.data(), (nCells + 1) * sizeof(int32_t));
+        if (source_tally)
+        {
+            size_t flat = 0;
+            for (const Domain& d : mc.domain)
+                for (int c = 0; c < d.nCells; ++c, ++flat) source_tally[flat] = d.sourceTally[c];
+        }
+        if (source_weight) *source_weight = weight;
+        if (split_factor) *split_factor = populationControlFactor(mc, n_census + (uint64_t)mc.sourceOffsets[nCells]);
+        return QSB_OK;
     });
 }
 
@@ -594,28 +640,9 @@ extern "C" int qsb_mc_cycle_init_resident(qsb_mc* h, qsb_ctx* ctx, qsb_cycle_ini
         mc.tallies.balanceTask[QSB_BAL_START] = mc.residentCensusCount;          // src/main.cc:106-110
         mc.tallies.scalarFluxSum = 0.0;
 
-        // source plan: per-cell counts (int)(cellWeight / weight), flat cell order; rebuilt only when the weight changes
-        // (a function of the deck and the time step only: evaluated once, it walks every cell of every rank)
-        if (mc.cachedSourceWeightDt != mc.timeStep) { mc.cachedSourceWeight = sourceParticleWeight(mc); mc.cachedSourceWeightDt = mc.timeStep; }
-        const double weight = mc.cachedSourceWeight;
+        const double weight = buildSourcePlan(mc);
         mc.sourceParticleWeight = weight;
         const size_t nCells = (size_t)mc.image.n_cells;
-        if (mc.sourceOffsets.size() != nCells + 1 || weight != mc.sourcePlanWeight)
-        {
-            mc.sourceOffsets.assign(nCells + 1, 0);
-            size_t flat = 0;
-            for (const Domain& d : mc.domain)
-                for (int c = 0; c < d.nCells; ++c, ++flat)
-                {
-                    const double cellWeight = d.volume[c] * mc.materialDatabase.mat[d.material[c]].sourceRate * mc.timeStep;
-                    const int n = (int)(cellWeight / weight);
-                    const int64_t next = (int64_t)mc.sourceOffsets[flat] + (n > 0 ? n : 0);
-                    if (next > INT32_MAX) throw std::runtime_error("more than 2^31 source particles on one rank");
-                    mc.sourceOffsets[flat + 1] = (int32_t)next;
-                }
-            mc.sourcePlanWeight = weight;
-            mc.sourcePlanId++;
-        }
         const uint64_t nSource = (uint64_t)mc.sourceOffsets[nCells];
 
         qsb_cycle_init_args a;

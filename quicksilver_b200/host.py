@@ -97,6 +97,16 @@ class MonteCarlo:
     def tracking_end_resident(self, ctx):
         self._check(self._lib.qsb_mc_tracking_end_resident(self._h, ctx._h))
 
+    def source_plan(self, n_census):
+        """(source_offsets[n_cells+1], source_tally[n_cells], source particle weight, split factor) of the coming cycle for a
+        rank whose carried-over census holds n_census particles -- what cycle_init_resident hands to the device."""
+        n = self.image.n_cells
+        off, tally = np.zeros(n + 1, dtype=np.int32), np.zeros(n, dtype=np.uint64)
+        w, f = C.c_double(), C.c_double()
+        self._check(self._lib.qsb_mc_source_plan(self._h, off.ctypes.data_as(C.POINTER(C.c_int32)), tally.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                 C.byref(w), C.byref(f), int(n_census)))
+        return off, tally, w.value, f.value
+
     def census_to_host(self, ctx):
         """bring the resident census back into the processed vault."""
         self._check(self._lib.qsb_mc_census_to_host(self._h, ctx._h))

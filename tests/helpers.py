@@ -76,6 +76,38 @@ class OracleResult:
     pass
 
 
+class _OracleCycleInitIO(C.Structure):
+    _fields_ = [("census", C.c_void_p), ("n_census", C.c_uint64), ("source_offsets", C.c_void_p), ("source_tally", C.c_void_p),
+                ("source_weight", C.c_double), ("e_min", C.c_double), ("e_max", C.c_double), ("time_step", C.c_double),
+                ("split_factor", C.c_double), ("low_weight_cutoff", C.c_double),
+                ("out", C.c_void_p), ("out_cap", C.c_uint64), ("n_out", C.c_uint64),
+                ("n_source", C.c_uint64), ("n_rr", C.c_uint64), ("n_split", C.c_uint64)]
+
+
+def oracle_cycle_init(image, census, source_offsets, source_tally, source_weight, e_min, e_max, dt, split_factor, low_weight_cutoff,
+                      strict=False):
+    """the oracle's stage-by-stage restatement of cycleInit (oracle/qs_oracle.c: qso_cycle_init): returns
+    (processing vault, n_source, n_rr, n_split)"""
+    lib = oracle_lib()
+    lib.qso_cycle_init.restype = C.c_int
+    lib.qso_cycle_init.argtypes = [C.POINTER(_capi.Image), C.c_int, C.POINTER(_OracleCycleInitIO)]
+    census = np.ascontiguousarray(census, dtype=PARTICLE_DTYPE)
+    off = np.ascontiguousarray(source_offsets, dtype=np.int32)
+    tally = np.ascontiguousarray(source_tally, dtype=np.uint64)
+    cap = int((len(census) + int(off[-1])) * max(2.0, split_factor + 2.0)) + 1024
+    out = np.zeros(cap, PARTICLE_DTYPE)
+    io = _OracleCycleInitIO()
+    io.census, io.n_census = census.ctypes.data, len(census)
+    io.source_offsets, io.source_tally = off.ctypes.data, tally.ctypes.data
+    io.source_weight, io.e_min, io.e_max, io.time_step = source_weight, e_min, e_max, dt
+    io.split_factor, io.low_weight_cutoff = split_factor, low_weight_cutoff
+    io.out, io.out_cap = out.ctypes.data, cap
+    rc = lib.qso_cycle_init(C.byref(image), int(strict), C.byref(io))
+    if rc != 0:
+        raise RuntimeError("qso_cycle_init failed: %d" % rc)
+    return out[:io.n_out].copy(), int(io.n_source), int(io.n_rr), int(io.n_split)
+
+
 def oracle_track(image, dt, particles, arrivals=None, strict=False, threads=1, census_cap=None, send_cap=None, want_flux=True):
     """Run the CPU restatement on a processing vault.  Returns census, sends, balance, flux."""
     lib = oracle_lib()

@@ -1,7 +1,7 @@
 """GPU parity tests of the device-resident cycle: cycleInit on the device -- MC_SourceNow +
 PopulationControl + RouletteLowWeightParticles (src/main.cc:96-121) in one kernel, population never leaving HBM --
-followed by the tracking kernel, against an ALL-CPU chain on the same deck: the host model's cycleInit (strict-math
-mode, the source the golden fixtures pin to the reference) + the oracle's tracking.
+followed by the tracking kernel, against an ALL-CPU chain on the same deck: the oracle's cycleInit (oracle/qs_oracle.c:
+qso_cycle_init, pinned against the reference's vault dumps by tests/test_oracle_golden.py) + the oracle's tracking, strict-math mode.
 
 Bit-exact bar: every integer balance column of every cycle (start, source, rr, split and the tracking tallies), and
 every census record byte for byte -- a census record is the end state of a history, so a single differing bit in a
@@ -31,17 +31,26 @@ CASES = {
 
 
 def cpu_chain(deck, cycles):
-    """host model (strict math) + oracle tracking: [(global row, flux sum, sorted census)] per cycle"""
+    """The all-CPU chain: the oracle's cycleInit (oracle/qs_oracle.c: qso_cycle_init, the reference's three stages one after
+    the other) + the oracle's tracking, both in strict-math mode.  The host model supplies the global numbers
+    (qsb_mc_source_plan) and keeps the books; its own cycleInit must produce the oracle's vault.
+    Returns [(global row, flux sum, sorted census, flux)] per cycle."""
     mc = host.MonteCarlo(["-i", deck])
     mc.set_strict_math(True)
-    dt = mc.get_double("dt")
+    dt, e_min, e_max, cutoff = (mc.get_double(k) for k in ("dt", "eMin", "eMax", "lowWeightCutoff"))
     out = []
+    census = np.zeros(0, H.PARTICLE_DTYPE)
     for _ in range(cycles):
+        off, tally, weight, factor = mc.source_plan(len(census))
+        vault, n_source, n_rr, n_split = H.oracle_cycle_init(mc.image, census, off, tally, weight, e_min, e_max, dt, factor, cutoff, strict=True)
         mc.cycle_init()
-        want = H.oracle_track(mc.image, dt, mc.processing(), strict=True, threads=1, want_flux=True)
+        assert H.sort_particles(mc.processing()).tobytes() == H.sort_particles(vault).tobytes()
+        want = H.oracle_track(mc.image, dt, vault, strict=True, threads=1, want_flux=True)
         mc.set_tracking_result(want.census, want.balance, want.flux.sum())
         row, flux = mc.cycle_finalize()
+        assert (int(row[BAL["source"]]), int(row[BAL["rr"]]), int(row[BAL["split"]])) == (n_source, n_rr, n_split)
         out.append((row.copy(), flux, H.sort_particles(want.census), want.flux))
+        census = want.census
     mc.close()
     return out
 

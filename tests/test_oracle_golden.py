@@ -297,3 +297,56 @@ def test_cycle_init_vault_is_identical_for_any_team_size(tmp_path):
                              env=dict(os.environ, QSB_HOST_THREADS=threads), timeout=600).stdout.strip()
         digests.add(out)
     assert len(digests) == 1, digests
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_cycle_init_equals_reference_vaults(case, tmp_path):
+    """oracle/qs_oracle.c: qso_cycle_init -- the stage-by-stage restatement of cycleInit (source, population control marching
+    backwards with erase-swap, low-weight roulette) -- against the vaults dumped from the reference (libm mode, byte for
+    byte after sorting by identifier) and against the host model's counts; the global numbers come from qsb_mc_source_plan."""
+    g = H.golden_case(case)
+    _, _, cycles, stored = make_golden.CASES[case]
+    mc = _model(case, tmp_path)
+    dt = mc.get_double("dt")
+    census = np.zeros(0, PARTICLE_DTYPE)
+    for c in range(stored):
+        off, tally, weight, factor = mc.source_plan(len(census))
+        vault, n_source, n_rr, n_split = H.oracle_cycle_init(mc.image, census, off, tally, weight, mc.get_double("eMin"), mc.get_double("eMax"), dt,
+                                                             factor, mc.get_double("lowWeightCutoff"), strict=False)
+        want_in = H.particles_from_bytes(g["cycle%d/tracking_input" % c])
+        assert weight == float(g["cycle%d/source_particle_weight" % c][0])
+        assert len(vault) == len(want_in)
+        assert H.sort_particles(vault).tobytes() == H.sort_particles(want_in).tobytes(), "cycle %d processing vault" % c
+        # the host model's own cycleInit: same vault, same counters
+        mc.cycle_init()
+        assert H.sort_particles(mc.processing()).tobytes() == H.sort_particles(vault).tobytes()
+        r = H.oracle_track(mc.image, dt, vault, strict=False, threads=1)
+        mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+        row, _ = mc.cycle_finalize()
+        assert (int(row[BAL["source"]]), int(row[BAL["rr"]]), int(row[BAL["split"]])) == (n_source, n_rr, n_split)
+        assert np.array_equal(row, g["cycle%d/balance" % c])
+        census = r.census
+
+
+def test_oracle_cycle_init_strict_mode_equals_host_strict_mode(tmp_path):
+    """strict-math mode (portable log/sin/cos): the oracle's cycleInit and the host model's agree bit for bit on the decks of
+    tests/test_gpu_resident.py -- the device cycle-init kernel is checked against the host model there, so it equals this
+    oracle too"""
+    from test_gpu_resident import CASES as RESIDENT_CASES
+    for name, (deck_name, over, cycles) in sorted(RESIDENT_CASES.items()):
+        deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
+        mc = host.MonteCarlo(["-i", deck])
+        mc.set_strict_math(True)
+        dt = mc.get_double("dt")
+        census = np.zeros(0, PARTICLE_DTYPE)
+        for c in range(min(cycles, 3)):
+            off, tally, weight, factor = mc.source_plan(len(census))
+            vault, n_source, n_rr, n_split = H.oracle_cycle_init(mc.image, census, off, tally, weight, mc.get_double("eMin"), mc.get_double("eMax"),
+                                                                 dt, factor, mc.get_double("lowWeightCutoff"), strict=True)
+            mc.cycle_init()
+            assert H.sort_particles(mc.processing()).tobytes() == H.sort_particles(vault).tobytes(), (name, c)
+            r = H.oracle_track(mc.image, dt, vault, strict=True, threads=os.cpu_count() or 1)
+            mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+            row, _ = mc.cycle_finalize()
+            assert (int(row[BAL["source"]]), int(row[BAL["rr"]]), int(row[BAL["split"]])) == (n_source, n_rr, n_split), (name, c)
+            census = r.census
