@@ -350,3 +350,37 @@ def test_oracle_cycle_init_strict_mode_equals_host_strict_mode(tmp_path):
             row, _ = mc.cycle_finalize()
             assert (int(row[BAL["source"]]), int(row[BAL["rr"]]), int(row[BAL["split"]])) == (n_source, n_rr, n_split), (name, c)
             census = r.census
+
+
+# ---- the strict-math chain (the checker of the GPU validation build) against the REFERENCE BINARY's tables -----------------
+
+HOMOGENEOUS_FLAGS = ["-X", "100", "-Y", "100", "-Z", "100", "-x", "16", "-y", "16", "-z", "16", "-I", "1", "-J", "1", "-K", "1", "-n", "40960"]
+STRICT_TABLES = [
+    ("CTS2_1", dict(nSteps=10), [], 10), ("Coral2_P1_1", dict(nSteps=10), [], 10), ("Coral2_P2_1", dict(nSteps=10), [], 10),
+    ("Homogeneous_v5", dict(nSteps=10), HOMOGENEOUS_FLAGS, 10), ("Homogeneous_v7", dict(nSteps=10), HOMOGENEOUS_FLAGS, 10),
+    ("NonFlatXC", dict(dt=5e-10, nParticles=100000, nSteps=5), [], 5),
+]
+
+
+@pytest.mark.parametrize("name,over,flags,cycles,strict_init",
+                         [t + (False,) for t in STRICT_TABLES] + [t + (True,) for t in STRICT_TABLES[1:2] + STRICT_TABLES[4:]])
+def test_strict_math_chain_reproduces_the_reference_binarys_tables(name, over, flags, cycles, strict_init, tmp_path):
+    """The GPU validation kernels are checked bit for bit against the oracle in strict-math mode (portable log/sin/cos);
+    the reference binary uses libm.  This closes the link between the two: at the Examples decks' LITERAL sizes the
+    strict-math chain -- host cycleInit in either math mode + qso_track(strict=1) -- prints the very table the unmodified
+    reference binary prints (tests/golden/balance_tables.json): all twelve integer columns of all
+    cycles, flux to the 7 printed digits.  tests/test_gpu_literal.py then holds the device to the same tables."""
+    golden = H.golden_table(name)
+    deck = decks.write_deck(decks.derive(name, over), str(tmp_path / "d.inp"))
+    mc = host.MonteCarlo(["-i", deck] + flags)
+    mc.set_strict_math(strict_init)
+    dt = mc.get_double("dt")
+    for c in range(cycles):
+        mc.cycle_init()
+        r = H.oracle_track(mc.image, dt, mc.processing(), strict=True, threads=os.cpu_count() or 1, want_flux=True)
+        mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+        row, flux = mc.cycle_finalize()
+        ints, _ = host.table_row(row, flux)
+        assert ints == golden[c][0], "%s cycle %d" % (name, c)
+        assert abs(flux - golden[c][1]) <= 1e-6 * abs(golden[c][1])
+    mc.close()
