@@ -10,9 +10,14 @@ host stages around it (cycleInit / cycleFinalize) run untimed between steps, as 
 value : segments / second, device-timed (CUDA events on the tracking stream), vault resident in HBM
 e2e   : the same metric through the drop-in call qsb_mc_cycle_tracking with HOST buffers: host vault ->
         device, tracking, census + tallies -> host, wall clock around the call
-One JSON line on stdout (rank 0).
+Beside the headline (Coral2_P1, fast build) the line carries: `validation_fom` (the bit-exact build on the same
+workload), `workloads` (CTS2, Coral2_P2, Homogeneous v5 / v7, NonFlatXC with and without the L2 window: every
+north_star config in one run), `parity_check` at N > 1 (the N-GPU run against the single-rank oracle chain),
+`cpu_baseline` / `reference_gpu` at N = 1 (the reference's OpenMP build and its own CUDA kernel recompiled for
+sm_100, same box).  One JSON line on stdout (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import re
@@ -29,8 +34,8 @@ sys.path.insert(0, ROOT)
 METRIC = "FOM segments/sec (cycle tracking)"
 UNIT = "segments/s"
 
-# per-GPU weak-scaled workloads: (deck, cells per side per GPU, box length per cell, particles per GPU,
-# algorithmic bytes per segment B_seg)
+# per-GPU weak-scaled workloads: deck, cells per side per GPU, box length per cell, particles per GPU,
+# algorithmic bytes per segment B_seg (the reference data model's bytes), deck overrides
 WORKLOADS = {
     "Coral2_P1": dict(deck="Coral2_P1", n=64, cell_len=1.0, particles=10485760, b_seg=2270.0),
     "Coral2_P2": dict(deck="Coral2_P2", n=44, cell_len=1.0 / 11.0, particles=3407360, b_seg=1930.0),
@@ -39,15 +44,18 @@ WORKLOADS = {
     # crossings), 32^3 cells of a 100 cm box, 3 276 800 particles; B_seg from the same formula (P_c = 0.97 / 0.29, L = 45.5)
     "Homogeneous_v5": dict(deck="Homogeneous_v5", n=32, cell_len=100.0 / 32.0, particles=3276800, b_seg=2258.0),
     "Homogeneous_v7": dict(deck="Homogeneous_v7", n=32, cell_len=100.0 / 32.0, particles=3276800, b_seg=1970.0),
+    # Examples/NonFlatXC/NonFlatXC.inp at its literal mesh and particle count; dt 1e-8 -> 5e-10 (as shipped the deck is
+    # explosively supercritical).  Two materials, 30 isotopes, energy-dependent cross sections: the
+    # 497 KB reaction table the persisting-L2 window exists for.  P_c = 0.85, 2 % facets; 9 x 30 table entries per collision.
+    "NonFlatXC": dict(deck="NonFlatXC", n=10, cell_len=10.0, particles=1000000, b_seg=3900.0, over=dict(dt=5e-10)),
 }
 GRID_LADDER = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
-# the reference's CPU run is timed on a bounded sample of the same deck: its own literal single-rank size
-REFERENCE_SAMPLE = {
-    "Coral2_P1": dict(n=16, particles=163840),
-    "Coral2_P2": dict(n=11, particles=53240),
-    "CTS2": dict(n=16, particles=40960),
-    "Homogeneous_v5": dict(n=16, particles=40960),
-    "Homogeneous_v7": dict(n=16, particles=40960),
+SECONDARY = ("CTS2", "Coral2_P2", "Homogeneous_v5", "Homogeneous_v7", "NonFlatXC")
+# cpu_baseline inside the B200 line: a bounded sample of the workload (same deck, same particles per cell, 1/8 of the cells)
+CPU_SAMPLE = {
+    "Coral2_P1": dict(n=32, particles=1310720), "Coral2_P2": dict(n=22, particles=425920), "CTS2": dict(n=32, particles=327680),
+    "Homogeneous_v5": dict(n=16, particles=409600), "Homogeneous_v7": dict(n=16, particles=409600),
+    "NonFlatXC": dict(n=10, particles=100000),
 }
 
 
@@ -96,46 +104,224 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def deck_argv(w, grid, tmpdir, n_steps):
+def size_flags(w, grid, n=None, particles=None):
+    gx, gy, gz = grid
+    n = n or w["n"]
+    particles = particles or w["particles"]
+    flags = ["-X", n * gx * w["cell_len"], "-Y", n * gy * w["cell_len"], "-Z", n * gz * w["cell_len"],
+             "-x", n * gx, "-y", n * gy, "-z", n * gz, "-I", gx, "-J", gy, "-K", gz, "-n", particles * gx * gy * gz]
+    return [str(a) for a in flags]
+
+
+def deck_argv(w, grid, tmpdir, n_steps, n=None, particles=None):
     """command line of one weak-scaled run: the reference's deck + its CLI size flags."""
     from quicksilver_b200 import decks
-    gx, gy, gz = grid
-    deck = decks.write_deck(decks.derive(w["deck"], nSteps=n_steps), os.path.join(tmpdir, "%s.inp" % w["deck"]))
-    n = w["n"]
-    argv = ["-i", deck, "-X", n * gx * w["cell_len"], "-Y", n * gy * w["cell_len"], "-Z", n * gz * w["cell_len"],
-            "-x", n * gx, "-y", n * gy, "-z", n * gz, "-I", gx, "-J", gy, "-K", gz, "-n", w["particles"] * gx * gy * gz]
-    return [str(a) for a in argv]
+    over = dict(w.get("over", {}), nSteps=n_steps)
+    deck = decks.write_deck(decks.derive(w["deck"], over), os.path.join(tmpdir, "%s.inp" % w["deck"]))
+    return ["-i", deck] + size_flags(w, grid, n, particles)
 
 
-def run_reference(workload, steps, warmup, threads=None):
-    """The reference's own CPU implementation (oracle/_ref/qs, built from the unmodified sources) on a
-    bounded sample of the workload: same deck, the reference's literal single-rank size."""
-    from quicksilver_b200 import decks
-    qs = os.path.join(ROOT, "oracle", "_ref", "qs")
-    if not os.path.exists(qs):
-        raise RuntimeError("oracle/_ref/qs missing: run __graft_entry__.build() where /root/reference exists")
-    s = REFERENCE_SAMPLE[workload]
-    w = WORKLOADS[workload]
-    threads = threads or os.cpu_count() or 1
-    with tempfile.TemporaryDirectory() as tmp:
-        deck = decks.write_deck(decks.derive(w["deck"], nSteps=steps + warmup), os.path.join(tmp, "ref.inp"))
-        n = s["n"]
-        argv = [qs, "-i", deck, "-X", n * w["cell_len"], "-Y", n * w["cell_len"], "-Z", n * w["cell_len"], "-x", n, "-y", n, "-z", n,
-                "-I", 1, "-J", 1, "-K", 1, "-n", s["particles"]]
-        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
-        t0 = time.time()
-        out = subprocess.run([str(a) for a in argv], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True).stdout
-        wall = time.time() - t0
-    segs, secs = 0, 0.0
+def host_cores():
+    """threads the CPU arms can use, and what the box has (state the core count)"""
+    logical = os.cpu_count() or 1
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = logical
+    physical = None
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False)
+    except Exception:
+        pass
+    return usable, {"usable_threads": usable, "logical_cpus": logical, "physical_cores": physical}
+
+
+def parse_cycle_table(out, skip):
+    """(segments, cycleTracking seconds, cycles) summed over the rows >= skip of the reference's cycle table"""
+    segs, secs, n = 0, 0.0, 0
     for line in out.splitlines():
         f = line.split()
-        if len(f) == 17 and f[0].isdigit() and int(f[0]) >= warmup:
+        if len(f) == 17 and f[0].isdigit() and int(f[0]) >= skip:
             segs += int(f[12])
             secs += float(f[15])
+            n += 1
+    return segs, secs, n
+
+
+def run_reference(workload, steps, warmup, n=None, particles=None, threads=None, exe=None, timeout=1500):
+    """The reference's own implementation (oracle/_ref/qs, the unmodified sources, OpenMP) on `workload` at n^3 cells /
+    `particles` (default: the workload's full per-GPU size); FOM from its own cycleTracking timer over the timed cycles."""
+    exe = exe or os.path.join(ROOT, "oracle", "_ref", "qs")
+    if not os.path.exists(exe):
+        raise RuntimeError("%s missing: run __graft_entry__.build() where /root/reference exists" % os.path.relpath(exe, ROOT))
+    w = WORKLOADS[workload]
+    n = n or w["n"]
+    particles = particles or w["particles"]
+    usable, _ = host_cores()
+    threads = threads or usable
+    with tempfile.TemporaryDirectory() as tmp:
+        argv = [exe] + deck_argv(w, (1, 1, 1), tmp, steps + warmup, n, particles)
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        t0 = time.time()
+        out = subprocess.run(argv, env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, check=True, timeout=timeout).stdout
+        wall = time.time() - t0
+    segs, secs, cycles = parse_cycle_table(out, warmup)
     value = segs / secs if secs > 0 else 0.0
-    sample = "%s at %d^3 cells, %d particles, %d cycles timed after %d warm-up (reference's cycleTracking timer)" % (
-        workload, s["n"], s["particles"], steps, warmup)
-    return value, threads, sample, secs, wall
+    sample = "%s at %d^3 cells, %d particles, %d cycles timed after %d warm-up (reference's cycleTracking timer)" % (workload, n, particles, cycles, warmup)
+    return {"value": value, "threads": threads, "sample": sample, "seconds": secs, "wall_s": wall, "cycles": cycles, "n": n, "particles": particles}
+
+
+def reference_line(args, warmup):
+    """`--impl reference`: the unmodified reference (OpenMP, all usable host threads) on the SAME per-GPU problem the B200 arm
+    runs at N = 1 (same_config true).  A full-size cycle takes the CPU tens of seconds, so the number of cycles is bounded
+    (1 warm-up + at most 2 timed: `cycles_timed` says so); the literal 16^3-cell deck size is reported beside it."""
+    usable, cores = host_cores()
+    w = WORKLOADS[args.workload]
+    timed = max(1, min(args.steps, 2))
+    n_full, p_full = w["n"], w["particles"]
+    if args.scale != 1.0:            # testing only (as for the B200 arm); reported in config
+        n_full = max(4, int(round(w["n"] * args.scale ** (1.0 / 3.0))))
+        p_full = int(w["particles"] * (n_full / w["n"]) ** 3)
+    full = run_reference(args.workload, timed, 1, n=n_full, particles=p_full)
+    small = None
+    try:
+        s = run_reference(args.workload, 5, 1, n=max(w["n"] // 4, 8), particles=max(w["particles"] // 64, 10000))
+        small = {"value": s["value"], "sample": s["sample"], "wall_s": round(s["wall_s"], 1)}
+    except Exception as e:
+        small = {"error": str(e)}
+    value = full["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": 1e3 * full["seconds"] / max(full["cycles"], 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %dx%dx%d cells and %d particles (the B200 arm's per-GPU problem at N = 1)" % (
+                           args.workload, n_full, n_full, n_full, p_full),
+                       "deck": w["deck"], "cells_per_gpu": n_full ** 3, "particles_per_gpu": p_full, "domain_grid": [1, 1, 1],
+                       "scale": args.scale, "same_config_as_b200_arm_at_n1": True, "cycles_timed": full["cycles"], "cycles_warmup": 1,
+                       "note": "reference CPU OpenMP build (oracle/_ref/qs, unmodified sources); a full-size cycle takes the CPU tens of "
+                               "seconds, so %d cycle(s) are timed instead of --steps %d" % (full["cycles"], args.steps)},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": full["threads"], "kind": "reference", "sample": full["sample"],
+                             "wall_s": round(full["wall_s"], 1), "host": cores},
+            "literal_deck_size": small,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def reference_gpu_block(workload):
+    """The reference's OWN CUDA variant (CycleTrackingKernel, src/main.cc:126-134 launched at :186-197; unified memory; one
+    thread per history; ~570 launches per CTS2 cycle) recompiled unmodified for sm_100 by oracle/Makefile `refcuda`
+    (BASELINE.md section 2b), run on this box's GPU 0: the same-box GPU number the new kernels have to beat."""
+    exe = os.path.join(ROOT, "oracle", "_ref_cuda", "qs_cuda")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref_cuda/qs_cuda not built (make -C oracle refcuda, needs /root/reference)"}
+    out = {"binary": "oracle/_ref_cuda/qs_cuda (reference sources, nvcc -DHAVE_CUDA -O2 -gencode arch=compute_100,code=sm_100)",
+           "regs": 164, "stack_bytes": 872, "runs": {}}
+    w = WORKLOADS[workload]
+    cases = [("literal_deck_size", max(w["n"] // 4, 8), max(w["particles"] // 64, 10000), 5, 2, 300),
+             ("same_config", w["n"], w["particles"], 2, 1, 420)]
+    for name, n, particles, steps, warm, limit in cases:
+        try:
+            r = run_reference(workload, steps, warm, n=n, particles=particles, threads=1, exe=exe, timeout=limit)
+            out["runs"][name] = {"value": r["value"], "unit": UNIT, "config": r["sample"], "wall_s": round(r["wall_s"], 1)}
+        except subprocess.TimeoutExpired:
+            out["runs"][name] = {"error": "did not finish within %d s" % limit}
+        except Exception as e:
+            out["runs"][name] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    best = out["runs"].get("same_config", {}).get("value") or out["runs"].get("literal_deck_size", {}).get("value")
+    out["value"] = best
+    out["config"] = "same_config" if out["runs"].get("same_config", {}).get("value") else "literal_deck_size"
+    return out
+
+
+def kernel_evidence(workload, scale):
+    """profiler evidence for the kernel that is LOADED: profiles/dram_traffic.json entries carry the hash of the kernel they
+    were captured from (qsb_kernel_hash); an entry taken from another kernel is refused (traffic null), never inherited."""
+    try:
+        from quicksilver_b200 import _capi
+        loaded = _capi.lib().qsb_kernel_hash().decode()
+    except Exception:
+        loaded = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            t = json.load(f).get(workload)
+    except Exception:
+        t = None
+    if not t or scale != 1.0:
+        return loaded, None, "no capture for this workload / size"
+    if t.get("kernel_hash") != loaded:
+        return loaded, None, "profiles/dram_traffic.json was captured from kernel %s, the loaded library is %s: refused" % (t.get("kernel_hash"), loaded)
+    return loaded, t, "ncu capture of this very kernel (hash %s)" % loaded
+
+
+def parity_block(rank, world, local_rank, dist, grid):
+    """N > 1, outside the timed region: the tests/test_gpu_multi.py case for this domain grid -- validation kernels, peer
+    exchange, 3 cycles -- against the single-rank CPU chain (host cycleInit + oracle tracking, strict math) of the same
+    global problem: cycle rows and the union of the ranks' census records, bit for bit.  The CHECKER leg runs the oracle
+    (rank 0 only); the product path never does."""
+    import numpy as np
+    import torch
+    from quicksilver_b200 import decks, driver
+    gx, gy, gz = grid
+    n, per_cell, cycles, deck_name = 8, 20, 3, "Coral2_P1"
+    tmp = tempfile.mkdtemp(prefix="qsb_parity_")
+    deck = decks.write_deck(decks.derive(deck_name, nSteps=cycles), os.path.join(tmp, "parity_r%d.inp" % rank))
+    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * world]
+    argv1 = [str(a) for a in ["-i", deck] + sizes + ["-I", 1, "-J", 1, "-K", 1]]
+    argvN = [str(a) for a in ["-i", deck] + sizes + ["-I", gx, "-J", gy, "-K", gz]]
+    out = {"n_ranks": world, "deck": deck_name, "global_cells": [n * gx, n * gy, n * gz], "particles": per_cell * n ** 3 * world,
+           "cycles": cycles, "kernels": "validation"}
+    err = ""
+    rows, census = [], []
+    try:
+        sim = driver.Simulation(argvN, rank, world, device=local_rank, validation=True, dist=dist, particle_capacity=1 << 20)
+        out["exchange"] = sim.exchange
+        gid = sim.mc.image.array("cell_gid")
+        for _ in range(cycles):
+            row, flux, _meta = sim.cycle()
+            rows.append([int(v) for v in row] + [float(flux)])
+            c, _, _ = sim.backend.results()
+            c = c.copy()
+            c["cell"] = gid[c["cell"]]
+            c["domain"] = 0
+            census.append(c)
+        sim.close()
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, e)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (err, [c.tobytes() for c in census]))
+    if rank != 0:
+        return None
+    errors = [g[0] for g in gathered if g[0]]
+    if errors:
+        out.update(rows_equal=False, census_equal=False, error=errors[0][:300])
+        return out
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        from quicksilver_b200 import host
+        mc = host.MonteCarlo(argv1)
+        dt = mc.get_double("dt")
+        gid1 = mc.image.array("cell_gid")
+        rows_equal = census_equal = True
+        for c in range(cycles):
+            mc.cycle_init()
+            r = H.oracle_track(mc.image, dt, mc.processing(), strict=True, threads=os.cpu_count() or 1)
+            mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+            row, flux = mc.cycle_finalize()
+            want = [int(v) for v in row]
+            rows_equal = rows_equal and rows[c][:13] == want and abs(rows[c][13] - flux) <= 1e-11 * abs(flux)
+            ref = r.census.copy()
+            ref["cell"] = gid1[ref["cell"]]
+            ref["domain"] = 0
+            union = np.concatenate([np.frombuffer(g[1][c], dtype=H.PARTICLE_DTYPE) for g in gathered])
+            census_equal = census_equal and H.sort_particles(union).tobytes() == H.sort_particles(ref).tobytes()
+        mc.close()
+        out.update(rows_equal=bool(rows_equal), census_equal=bool(census_equal), census_records_last_cycle=int(len(union)),
+                   checker="single-rank host cycleInit + oracle/liboracle.so qso_track(strict=1)")
+    except Exception as e:
+        out.update(rows_equal=False, census_equal=False, error="checker failed: %s: %s" % (type(e).__name__, str(e)[:300]))
+    return out
 
 
 def main():
@@ -148,6 +334,7 @@ def main():
     ap.add_argument("--fast", type=int, default=1, help="1: fast build kernels (default), 0: validation build")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the per-GPU problem (testing only; reported in config)")
     ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--extras", type=int, default=1, help="0: headline only (no validation_fom / workloads / parity_check / reference_gpu)")
     ap.add_argument("--resident-only", type=int, default=0,
                     help="1: skip the host-buffer (e2e) pass -- for ncu runs only: under the profiler a kernel launch does not return "
                          "until the kernel has ended, so the streamed pass (kernel launched first, then fed by DMA) cannot make progress")
@@ -161,78 +348,124 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        value, threads, sample, secs, _ = run_reference(args.workload, args.steps, warmup)
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "note": "reference CPU OpenMP build, bounded sample of the workload"},
-                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
-                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        return reference_line(args, warmup)
 
     if world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
     import torch
     from quicksilver_b200 import driver
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % local_rank))
 
-    result = driver.run_benchmark(args, warmup, rank, world, local_rank, WORKLOADS, GRID_LADDER, deck_argv, ClockSampler)
+    result = driver.run_benchmark(args, warmup, rank, world, local_rank, WORKLOADS, GRID_LADDER, deck_argv, ClockSampler, dist=dist)
+
+    # ---- beside the headline, outside its timed region -----------------------------------------------------------------
+    extras = {}
+    grid = GRID_LADDER[world]
+    if args.extras and not args.resident_only and args.scale == 1.0:
+        tmp = tempfile.mkdtemp(prefix="qsb_bench_extra_")
+
+        def resident(name, validation, warm, steps, env=None):
+            try:
+                w = WORKLOADS[name]
+                return driver.run_resident_workload(deck_argv(w, grid, tmp, warm + steps), rank, world, local_rank, dist, validation, warm, steps, env=env)
+            except Exception as e:
+                return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+        # the bit-exact build on the headline workload: the price of --fmad=false + IEEE div/sqrt + the exact facet predicate
+        extras["validation_fom"] = resident(args.workload, True, 1, 3)
+        extras["workloads"] = {}
+        for name in SECONDARY:
+            if name != args.workload:
+                extras["workloads"][name] = resident(name, not args.fast, 2, 5)
+        # NonFlatXC again with the hot block left to the ordinary L2 policy: what the persisting window buys (north_star:
+        # "pinned in Blackwell's ~126 MB L2 via an access-policy window")
+        extras["workloads"]["NonFlatXC_no_l2_window"] = resident("NonFlatXC", not args.fast, 2, 5, env={"QSB_NO_L2_WINDOW": "1"})
+        if world > 1:
+            extras["parity_check"] = parity_block(rank, world, local_rank, dist, grid)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
+
     peak, peak_src = measured_peak()
     w = WORKLOADS[args.workload]
-    # DRAM bytes of one full-size launch of the tracking kernel, from the committed ncu capture (None for other sizes)
-    try:
-        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            t = json.load(f).get(args.workload)
-        result["traffic"] = t["dram_bytes_per_launch"] if (t and args.scale == 1.0) else None
-        result["issue_bound_evidence"] = t.get("issue_bound_evidence") if t else None
-    except Exception:
-        result["traffic"] = None
+    kernel_hash, evidence, evidence_note = kernel_evidence(args.workload, args.scale)
+    traffic = evidence["dram_bytes_per_launch"] if evidence else None
     kernel_s = result["kernel_seconds_max"]
-    achieved = w["b_seg"] * result["segments_rank0"] / result["kernel_seconds_rank0"] / 1e9 if result["kernel_seconds_rank0"] > 0 else 0.0
+    seg_rank0, ks_rank0 = result["segments_rank0"], result["kernel_seconds_rank0"]
+    achieved = w["b_seg"] * seg_rank0 / ks_rank0 / 1e9 if ks_rank0 > 0 else 0.0
+    dev_ms = result["tracking_ms_per_step_rank0"]["cuda_events_on_kernel_stream"]
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "peak_source": peak_src, "kernel": "track_kernel", "kernel_hash": kernel_hash, "evidence": evidence_note,
+            # what the kernel really moves: ncu DRAM bytes of one full-size launch of THIS kernel / this run's launch time
+            "dram_achieved": (traffic / (1e-3 * dev_ms) / 1e9) if traffic and world == 1 and dev_ms > 0 else None,
+            "algorithmic_bytes_per_segment": w["b_seg"],
+            "algorithmic_bytes_per_launch": w["b_seg"] * seg_rank0 / max(args.steps, 1),
+            "note": "achieved = SURVEY 8(d) yardstick (bytes the REFERENCE's data model touches per segment) x segments / kernel time; "
+                    "it exceeds the HBM peak because the 64-byte cell record + per-material cross-section table replace the "
+                    "reference's 1.8 KB of geometry per segment (results bit-identical); `traffic` is what the kernel really "
+                    "moves (ncu) -- the kernel is latency / issue bound: `issue_frac` is the ceiling that applies, see DESIGN.md section 5"}
+    if roof["dram_achieved"]:
+        roof["dram_frac"] = roof["dram_achieved"] / peak
+    if evidence and evidence.get("thread_instructions_per_segment") and dev_ms > 0 and world == 1:
+        # the stated ceiling of this latency-bound kernel: thread-instructions retired / (148 SMs x 4 schedulers x 32 lanes x clock)
+        clock_hz = 1e6 * float((result.get("clocks") or {}).get("sm_mhz") or 1965.0)
+        seg_per_launch = seg_rank0 / max(args.steps, 1)
+        lane_slots = 148 * 4 * 32 * clock_hz * (1e-3 * dev_ms)
+        roof["issue_frac"] = evidence["thread_instructions_per_segment"] * seg_per_launch / lane_slots
+        roof["issue_frac_note"] = "thread-instructions per segment (ncu, this kernel) x segments per launch / (148 x 4 x 32 lane-issue slots per cycle x SM clock x launch time)"
+    if evidence and evidence.get("issue_bound_evidence"):
+        roof["issue_bound_evidence"] = evidence["issue_bound_evidence"]
+
     line = {"metric": METRIC, "value": result["segments_total"] / kernel_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": 1e3 * kernel_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": result["config"],
             "clocks": result["clocks"],
             "e2e": {"value": result["segments_total"] / result["e2e_seconds_max"], "unit": UNIT,
-                    "h2d_bytes_per_step": result["h2d_bytes_per_step"], "d2h_bytes_per_step": result["d2h_bytes_per_step"]},
+                    "h2d_bytes_per_step": result["h2d_bytes_per_step"], "d2h_bytes_per_step": result["d2h_bytes_per_step"],
+                    "host_gbs_aggregate": (result["h2d_bytes_per_step"] + result["d2h_bytes_per_step"]) * args.steps / result["e2e_seconds_max"] / 1e9},
             "gpu_launches": result["gpu_launches"],
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": result.get("traffic"), "peak_source": peak_src, "kernel": "track_kernel",
-                         # what the kernel really moves: ncu DRAM bytes of one full-size launch / this run's launch time
-                         "dram_achieved": (result["traffic"] / (1e-3 * result["tracking_ms_per_step_rank0"]["cuda_events_on_kernel_stream"]) / 1e9)
-                                          if result.get("traffic") and world == 1 else None,
-                         "algorithmic_bytes_per_segment": w["b_seg"],
-                         "algorithmic_bytes_per_launch": w["b_seg"] * result["segments_rank0"] / max(args.steps, 1),
-                         "note": "achieved = SURVEY 8(d) yardstick (bytes the REFERENCE's data model touches per segment) x segments / kernel time; "
-                                 "it exceeds the HBM peak because the 64-byte cell record + per-material cross-section table replace the "
-                                 "reference's 1.8 KB of geometry per segment (results bit-identical); `traffic` is what the kernel really "
-                                 "moves (ncu), ~32 B/segment -- the kernel is latency / issue bound, see DESIGN.md section 5"},
+            "roofline": roof,
             "tracking_ms_per_step_rank0": result["tracking_ms_per_step_rank0"],
             "whole_cycle": result.get("whole_cycle"),
             "balance_check": result["balance_check"]}
-    if result.get("issue_bound_evidence"):
-        # the kernel is issue / latency bound, not HBM bound: the ncu numbers that say so, from the committed digest
-        line["roofline"]["issue_bound_evidence"] = result["issue_bound_evidence"]
-    if line["roofline"]["dram_achieved"]:
-        line["roofline"]["dram_frac"] = line["roofline"]["dram_achieved"] / peak
+    if result.get("per_rank"):
+        line["per_rank"] = result["per_rank"]
+    vf = extras.get("validation_fom")
+    if vf:
+        line["validation_fom"] = vf.get("value") if "value" in vf else None
+        line["validation_build"] = vf
+    for key in ("workloads", "parity_check"):
+        if extras.get(key) is not None:
+            line[key] = extras[key]
     wc = result.get("whole_cycle") or {}
     if isinstance(wc.get("resident"), dict) and wc["resident"].get("cycle_init_kernel_ms_rank0"):
-        # the HBM-bound kernel of the resident cycle: 164 B read + 168 B written per particle
+        # the HBM-bound kernel of the resident cycle: every particle's 168-byte record is written; only the
+        # carried-over (census) particles are READ (164 B) -- the source particles are made in registers
         r = wc["resident"]
         n_part = result["h2d_bytes_per_step"] / 136.0
-        gbs = n_part * 332.0 / (r["cycle_init_kernel_ms_rank0"] * 1e-3) / 1e9
+        n_read = r.get("carried_per_cycle") or 0.9 * n_part
+        gbs = (n_read * 164.0 + n_part * 168.0) / (r["cycle_init_kernel_ms_rank0"] * 1e-3) / 1e9
         r["cycle_init_roofline"] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "kernel": "cycle_init_kernel",
-                                    "algorithmic_bytes_per_particle": 332, "particles_per_launch": n_part}
+                                    "algorithmic_bytes": "164 B read per carried particle + 168 B written per particle",
+                                    "particles_written_per_launch": n_part, "particles_read_per_launch": n_read}
     if args.cpu_baseline and world == 1:
+        _, cores = host_cores()
         try:
-            value, threads, sample, _, wall = run_reference(args.workload, 5, 1)
-            line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample,
-                                    "wall_s": round(wall, 1)}
+            s = CPU_SAMPLE[args.workload]
+            r = run_reference(args.workload, 3, 1, n=s["n"], particles=s["particles"])
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "reference", "sample": r["sample"],
+                                    "wall_s": round(r["wall_s"], 1), "host": cores}
         except Exception as e:  # the baseline is reported, never required for the GPU number
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % e}
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "failed: %s" % e, "host": cores}
+        if args.extras and not args.resident_only:
+            line["reference_gpu"] = reference_gpu_block(args.workload)
     print(json.dumps(line))
     return 0
 

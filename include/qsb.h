@@ -214,7 +214,7 @@ typedef struct qsb_options {
     int32_t  tracking_mode;     /* bit 0 reserved (0: history-based persistent kernel); bit 1 (value 2): run the
                                    filtered and the full nearest-facet search side by side and count mismatches;
                                    bit 2 (value 4): likewise for the direct reaction selection vs the subtraction chain */
-    uint64_t particle_capacity; /* SoA slots per vault; 0 = derive from nParticles and nuBar            */
+    uint64_t particle_capacity; /* SoA slots per vault; 0 = 1 << 20 (callers size it: nParticles x (3 + 2 nuBar)) */
     uint64_t send_capacity;     /* slots per peer send/recv slab; 0 = derive                             */
     int32_t  threads_per_block; /* 0 = default                                                           */
     int32_t  blocks_per_sm;     /* 0 = default                                                           */
@@ -326,11 +326,19 @@ int  qsb_peer_export(qsb_ctx* ctx, void* handle /* [QSB_PEER_HANDLE_BYTES] */, u
 int  qsb_peer_connect(qsb_ctx* ctx, const void* handles /* [n_ranks][QSB_PEER_HANDLE_BYTES], rank order */, int n_ranks,
                       double watchdog_seconds);
 int  qsb_peer_disconnect(qsb_ctx* ctx);
+/* timings of the last peer-mode qsb_track on this rank, measured on the device: [0] kernel start -> this GPU first had nothing
+ * queued or running (ns), [1] kernel start -> global termination seen (ns), [2] SM cycles its warps spent depositing particles
+ * on peers (summed over warps), [3] deposit passes, [4] wait for the peers' launch at kernel start (ns), [5] tickets used,
+ * [6] particles deposited on peers, [7] reserved (0).  The tail of a cycle is [1] - [0]. */
+int  qsb_peer_diagnostics(qsb_ctx* ctx, uint64_t out[8]);
 const char* qsb_last_error(qsb_ctx* ctx);
 /* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] check-mode (geometry or reaction)
  * disagreements (check mode; must be 0), [2] reaction-table entries scanned, [3] compact geometry enabled,
  * [4] registers per thread, [5] resident blocks per SM, [6] grid size, [7] vault slots used. */
 int  qsb_get_diagnostics(qsb_ctx* ctx, uint64_t out[8]);
+/* 16 hex digits naming the tracking kernels this library was built from (their sources + tuning knobs): profiler evidence
+ * is recorded against it (profiles/dram_traffic.json) and bench.py refuses evidence taken from another kernel */
+const char* qsb_kernel_hash(void);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t qsb_launch_count(qsb_ctx* ctx);
 

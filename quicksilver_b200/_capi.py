@@ -167,6 +167,8 @@ def _declare(lib):
         "qsb_last_error": (C.c_char_p, [vp]),
         "qsb_launch_count": (C.c_uint64, [vp]),
         "qsb_get_diagnostics": (C.c_int, [vp, u64p]),
+        "qsb_peer_diagnostics": (C.c_int, [vp, u64p]),
+        "qsb_kernel_hash": (C.c_char_p, []),
         "qsb_mc_cycle_tracking": (C.c_int, [vp, vp, _P(TrackStats)]),
         "qsb_mc_tracking_begin": (C.c_int, [vp, vp]),
         "qsb_mc_tracking_end": (C.c_int, [vp, vp]),

@@ -316,6 +316,10 @@ extern "C" {
 
 const char* qsb_last_error(qsb_ctx* c) { return c ? c->error.c_str() : g_create_error.c_str(); }
 uint64_t qsb_launch_count(qsb_ctx* c) { return c ? c->launches : 0; }
+#ifndef QSB_KERNEL_HASH
+#define QSB_KERNEL_HASH "unknown"
+#endif
+const char* qsb_kernel_hash(void) { return QSB_KERNEL_HASH; }
 uint64_t qsb_exchange_record_bytes(void) { return sizeof(ExchangeRecord); }
 
 int qsb_create(int device, const qsb_image* image, double time_step, const qsb_options* opt, qsb_ctx** out)
@@ -353,6 +357,10 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         QSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
 
         // ---- image ----
+        // a fission emits (int)(nuBar + r) neutrons, r in [0, 1): the kernel holds at most 4 (energy, angle) pairs per collision
+        // (the reference's MAX_PRODUCTION_SIZE assert, src/CollisionEvent.cc:95-97, is 4 as well)
+        for (int m = 0; m < image->n_materials; ++m)
+            if (!(image->mat_nu_bar[m] < 4.0)) throw CudaFailure{ "image: a material's nuBar is 4 or more; at most 4 neutrons per fission are supported" };
         const size_t nc = image->n_cells, ng = image->n_groups, nm = image->n_materials, mr = image->max_reactions_per_material;
         DevImage& im = c->im;
         im.n_cells = image->n_cells; im.n_groups = image->n_groups; im.n_materials = image->n_materials;
@@ -462,7 +470,8 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         // pin the hot block in L2 (126 MB on B200): persisting carve-out + access-policy window on our stream
         {
             size_t want = std::min<size_t>(hot_bytes, (size_t)prop.persistingL2CacheMaxSize);
-            if (want > 0 && prop.accessPolicyMaxWindowSize > 0)
+            // QSB_NO_L2_WINDOW=1: leave the hot block to the ordinary L2 replacement policy (bench.py's NonFlatXC A/B)
+            if (want > 0 && prop.accessPolicyMaxWindowSize > 0 && std::getenv("QSB_NO_L2_WINDOW") == nullptr)
             {
                 cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
                 cudaStreamAttrValue attr{};
@@ -497,6 +506,9 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
 
         // ---- launch shape: persistent grid, resident blocks per SM from the occupancy calculator ----
         c->block = c->opt.threads_per_block > 0 ? c->opt.threads_per_block : 128;
+        // the kernel is compiled with __launch_bounds__(128) and uses full-mask warp intrinsics throughout
+        if (c->block < 32 || c->block > 128 || (c->block & 31) != 0)
+            throw CudaFailure{ "qsb_options.threads_per_block must be a multiple of 32 between 32 and 128" };
         if (c->opt.validation) track_kernel_attributes_validation(&c->regs, &c->blocks_per_sm, c->block);
         else                   track_kernel_attributes_fast(&c->regs, &c->blocks_per_sm, c->block);
         check(cudaGetLastError(), "kernel attributes (is the sm_100a image loadable on this device?)");
@@ -510,9 +522,9 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
     catch (const CudaFailure& f)
     {
         g_create_error = f.what;
-        for (void* p : c->owned) cudaFree(p);
-        delete c;
-        return QSB_ERR_CUDA;
+        const bool bad_arg = f.what.rfind("qsb_options.", 0) == 0 || f.what.rfind("image:", 0) == 0;
+        qsb_destroy(c);             // frees device + page-locked allocations, streams and events created so far
+        return bad_arg ? QSB_ERR_ARG : QSB_ERR_CUDA;
     }
     *out = c;
     return QSB_OK;
@@ -793,13 +805,8 @@ void issueStreamInput(qsb_ctx* c)
     if (c->stream_input_issued || c->n_in_aos == 0) { c->stream_input_issued = true; return; }
     c->stream_input_issued = true;
     const unsigned long long n = c->n_in_aos;
-    const size_t n_chunks = (n + kInputChunkRecords - 1) / kInputChunkRecords;
-    if (n_chunks > c->n_marks)
-    {
-        if (c->h_marks) cudaFreeHost(c->h_marks);
-        c->n_marks = n_chunks + 64;
-        QSB_CUDA(cudaMallocHost((void**)&c->h_marks, c->n_marks * sizeof(unsigned long long)));
-    }
+    // (h_marks was sized by qsb_stream_begin: page-locked allocation / free synchronise implicitly with the running kernel,
+    //  which at this point is spinning on the very marks this function is about to enqueue)
     const bool pinned = isPinnedHost(c->host_in);
     const size_t half = c->staging_records / 2;
     size_t k = 0;
@@ -879,6 +886,20 @@ int qsb_stream_begin(qsb_ctx* c, const qsb_base_particle* in, uint64_t n_in, qsb
             std::memset(c->h_chunk_flags, 0, c->n_chunks * sizeof(unsigned int));
             QSB_CUDA(cudaHostGetDevicePointer((void**)&c->d_chunk_flags, c->h_chunk_flags, 0));
         }
+        {
+            // one in_ready mark per input copy; a pageable source is staged through half the bounce buffer per copy.  Sized
+            // here, BEFORE the tracking kernel is launched: cudaMallocHost / cudaFreeHost may block until a running kernel ends,
+            // and the kernel cannot end before the marks have been enqueued.
+            const size_t per_copy = std::min(kInputChunkRecords, std::max<size_t>(c->staging_records / 2, 1));
+            const size_t need = (size_t)((n_in + per_copy - 1) / per_copy) + 1;
+            if (need > c->n_marks)
+            {
+                QSB_CUDA(cudaStreamSynchronize(c->stream_in));
+                if (c->h_marks) { QSB_CUDA(cudaFreeHost(c->h_marks)); c->h_marks = nullptr; c->n_marks = 0; }
+                QSB_CUDA(cudaMallocHost((void**)&c->h_marks, (need + 64) * sizeof(unsigned long long)));
+                c->n_marks = need + 64;
+            }
+        }
         QSB_CUDA(cudaMemsetAsync(c->d_chunk_done, 0, c->n_chunks * sizeof(unsigned int), c->stream));
         c->streaming = true; c->stream_input_issued = false;
         c->host_in = in; c->n_in_aos = n_in;
@@ -936,6 +957,7 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             c->h_peer->epoch = c->peer_epoch;
             QSB_CUDA(cudaMemcpyAsync(&d_peer->inflight, &c->h_peer->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
             QSB_CUDA(cudaMemcpyAsync(&d_peer->tail, &c->h_peer->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            QSB_CUDA(cudaMemsetAsync(&d_peer->first_idle_ns, 0, 5 * sizeof(unsigned long long), c->stream));          // this launch's diagnostics
             QSB_CUDA(cudaMemcpyAsync(&d_peer->n_in, &c->h_peer->n_in, 16, cudaMemcpyHostToDevice, c->stream));        // n_in + vault_epoch + epoch
         }
         if (c->streaming && !c->stream_input_issued)
@@ -983,7 +1005,6 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
                              "send_advance: %llu calls, %.1f Mcycles over all warps; start-up wait %.3f ms\n",
                              c->my_rank, c->peer_epoch, ms, c->h_peer->first_idle_ns * 1e-6, c->h_peer->done_ns * 1e-6, c->h_peer->tail,
                              c->h_peer->send_calls, c->h_peer->send_cycles * 1e-6, c->h_peer->startup_wait_ns * 1e-6);
-                QSB_CUDA(cudaMemset(&reinterpret_cast<PeerControl*>(c->peer_block)->send_cycles, 0, 16));
             }
             if (c->h_peer->abort == c->peer_epoch)
             {
@@ -1016,6 +1037,8 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             c->error = msg;
             return (int)QSB_ERR_CAPACITY;
         }
+        if (c->h_ctl->bad_group)
+        { c->error = "a particle's energy lies above the last energy-group edge (eMax below the fission spectrum's 20 MeV?); the reference's behaviour there is undefined"; return (int)QSB_ERR_INTERNAL; }
         if (c->h_ctl->bad_reaction)
         { c->error = "a collision selected no reaction (cross-section table inconsistent)"; return (int)QSB_ERR_INTERNAL; }
         return (int)QSB_OK;
@@ -1238,6 +1261,19 @@ int qsb_peer_connect(qsb_ctx* c, const void* handles, int n_ranks, double watchd
         }
         c->watchdog_ns = (unsigned long long)((watchdog_seconds > 0 ? watchdog_seconds : 60.0) * 1e9);
         c->peer_on = std::getenv("QSB_DEBUG_PEER_MAP_ONLY") == nullptr;      // experiment: mappings in place, exchange left to the caller
+        return (int)QSB_OK;
+    });
+}
+
+int qsb_peer_diagnostics(qsb_ctx* c, uint64_t out[8])
+{
+    if (!out) return QSB_ERR_ARG;
+    return guarded(c, [&]() {
+        if (!c->h_peer) { c->error = "qsb_peer_diagnostics before qsb_peer_export"; return (int)QSB_ERR_STATE; }
+        unsigned long long sent = 0;
+        for (int r = 0; r < c->n_ranks; ++r) sent += c->h_ctl->send_count[r];
+        out[0] = c->h_peer->first_idle_ns; out[1] = c->h_peer->done_ns; out[2] = c->h_peer->send_cycles; out[3] = c->h_peer->send_calls;
+        out[4] = c->h_peer->startup_wait_ns; out[5] = c->h_peer->tail; out[6] = sent; out[7] = 0;
         return (int)QSB_OK;
     });
 }

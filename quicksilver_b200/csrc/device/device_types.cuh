@@ -103,7 +103,7 @@ struct DevControl
     unsigned int overflow;              // bit0 processing vault, bit1 census vault, bit2 send slab
     unsigned int bad_reaction;          // collisions where no reaction was selected (reference: unreachable)
     unsigned int epoch;
-    unsigned int pad;
+    unsigned int bad_group;             // particles whose energy lies above the last group edge (the reference indexes out of bounds there)
     unsigned long long send_count[64];  // per peer rank
 };
 

@@ -209,12 +209,17 @@ __device__ __forceinline__ double m_sqrt(double x) { return approx_sqrt(x); }
 // estimated from a single-precision log2 and then corrected against the table itself -- the answer is decided by
 // the same comparisons on the same doubles, so it is the reference's for ANY increasing table; a bad estimate only costs
 // extra steps.  Two dependent loads instead of eight.
-__device__ __forceinline__ int energy_group(const DevImage& im, double energy)
+// Above the last edge the reference returns nGroups, one past the last group, and then indexes its tables with it
+// (undefined behaviour on the host; here it would be a stray flux tally or an illegal address).  Reachable only when a
+// deck's eMax is below the 20 MeV a fission neutron can carry (src/NuclearData.cc:77): the particle is put in the last
+// group and counted, and qsb_track reports the cycle as failed.
+__device__ __forceinline__ int energy_group(const TrackArgs& a, double energy)
 {
+    const DevImage& im = a.im;
     const int n = im.n_groups + 1;
     const double* __restrict__ e = im.energies;
     if (energy <= __ldg(e)) return 0;
-    if (energy > __ldg(e + n - 1)) return n - 1;
+    if (__builtin_expect(energy > __ldg(e + n - 1), 0)) { atomicAdd(&a.ctl->bad_group, 1u); return n - 2; }
     int i = (int)((__log2f((float)energy) - im.group_log2_lo) * im.group_inv_dlog2);
     i = min(max(i, 0), n - 2);
     while (i > 0 && energy < __ldg(e + i)) --i;
@@ -226,7 +231,7 @@ __device__ __forceinline__ double speed_of(const Particle& p) { return m_sqrt(p.
 
 // MC_Load_Particle + MC_Particle(const MC_Base_Particle&): src/MC_Load_Particle.cc:11-29,
 // src/MC_Base_Particle.hh:287-331
-__device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p, double dt, bool derive_direction)
+__device__ __forceinline__ void reload_transform(const TrackArgs& a, Particle& p, double dt, bool derive_direction)
 {
     p.speed = speed_of(p);
     if (derive_direction)
@@ -236,7 +241,7 @@ __device__ __forceinline__ void reload_transform(const DevImage& im, Particle& p
     }
     if (p.ttc <= 0.0) p.ttc += dt;
     if (p.age < 0.0) p.age = 0.0;
-    p.group = energy_group(im, p.energy);
+    p.group = energy_group(a, p.energy);
 }
 
 __device__ __forceinline__ int load_particle(const TrackArgs& a, unsigned long long i, Particle& p)
@@ -254,7 +259,7 @@ __device__ __forceinline__ int load_particle(const TrackArgs& a, unsigned long l
     p.facet = 0; p.total_xs = 0.0;
     p.head = load_cell_head(a.im, p.cell);
     if (p.last_event == kRawChild) { p.last_event = QSB_EV_COLLISION; p.speed = 0.0; p.group = 0; return kStateTail; }
-    reload_transform(a.im, p, a.dt, p.alpha != p.alpha);
+    reload_transform(a, p, a.dt, p.alpha != p.alpha);
     return kStateSegment;
 }
 
@@ -276,7 +281,7 @@ __device__ __forceinline__ void load_particle_aos(const TrackArgs& a, unsigned l
     p.cell = __ldg(a.im.domain_cell_offset + domain) + cell;
     p.facet = 0; p.total_xs = 0.0;
     p.head = load_cell_head(a.im, p.cell);
-    reload_transform(a.im, p, a.dt, true);
+    reload_transform(a, p, a.dt, true);
 }
 
 __device__ __forceinline__ void store_particle(const VaultView& v, unsigned long long i, const Particle& p, bool with_direction)
@@ -906,7 +911,7 @@ __device__ __forceinline__ void collision_tail(const TrackArgs& a, Particle& p, 
         if (p.ttc <= 0.0) p.ttc += a.dt;
         if (p.age < 0.0) p.age = 0.0;
     }
-    p.group = energy_group(a.im, p.energy);
+    p.group = energy_group(a, p.energy);
 }
 
 // ---- facet crossing --------------------------------------------------------------------------------------

@@ -166,5 +166,12 @@ class DeviceContext:
                 "blocks_per_sm", "grid", "vault_slots_used")
         return {k: int(v) for k, v in zip(keys, out)}
 
+    def peer_diagnostics(self):
+        """device-side timings of the last peer-mode launch (qsb_peer_diagnostics)"""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.qsb_peer_diagnostics(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        keys = ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "tickets", "deposited")
+        return {k: int(v) for k, v in zip(keys, out)}
+
     def launch_count(self):
         return int(self._lib.qsb_launch_count(self._h))

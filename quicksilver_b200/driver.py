@@ -173,21 +173,31 @@ def exchange_rounds(backend, dist, rank, world, max_rounds=100000):
 def bind_to_gpu_numa_node(device):
     """Run this process (and therefore first-touch its page-locked vaults) on the CPUs of the NUMA node the GPU hangs off, so
     that the streamed host vaults do not cross the socket interconnect on their way to and from the device.  Several ranks
-    of one node otherwise land wherever the scheduler puts them.  Best effort: returns the node, or None if anything about
-    the topology cannot be read (no sysfs, no nvidia-smi, a single node)."""
+    of one node otherwise land wherever the scheduler puts them.  Best effort: returns (node, why): node is None when nothing
+    was bound, and `why` says what stood in the way (bench.py prints it as numa_node_rank0 / numa_note)."""
     import os
     import subprocess
     if os.environ.get("QSB_NO_NUMA_BIND"):
-        return None
+        return None, "QSB_NO_NUMA_BIND set"
     try:
         out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout.strip().splitlines()[0].strip()
         dom, rest = out.split(":", 1)                      # "00000000:1B:00.0" -> "0000:1b:00.0"
         bdf = ("%04x:%s" % (int(dom, 16), rest)).lower()
+    except Exception as e:
+        return None, "nvidia-smi gave no PCI bus id (%s)" % type(e).__name__
+    try:
         with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
             node = int(f.read().strip())
-        if node < 0:
-            return None
+    except Exception:
+        return None, "no /sys/bus/pci/devices/%s/numa_node in this container" % bdf
+    if node < 0:
+        try:
+            n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+        except Exception:
+            n_nodes = 0
+        return None, "the platform reports numa_node = -1 for %s (%d NUMA node(s) visible): nothing to bind to" % (bdf, n_nodes)
+    try:
         with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
             cpus = set()
             for part in f.read().strip().split(","):
@@ -195,11 +205,11 @@ def bind_to_gpu_numa_node(device):
                 cpus.update(range(int(lo), int(hi or lo) + 1))
         allowed = os.sched_getaffinity(0) & cpus
         if not allowed:
-            return None
+            return None, "none of NUMA node %d's CPUs is in this process's affinity mask (cgroup cpuset)" % node
         os.sched_setaffinity(0, allowed)
-        return node
-    except Exception:
-        return None
+        return node, "bound to %d CPUs of node %d" % (len(allowed), node)
+    except Exception as e:
+        return None, "could not read / apply the CPU list of node %d (%s)" % (node, type(e).__name__)
 
 
 class Simulation:
@@ -214,7 +224,7 @@ class Simulation:
         self.rank, self.world, self.dist = rank, world, dist
         self.resident = bool(resident) and make_backend is None
         self.torch_device = "cuda:%d" % device
-        self.numa_node = bind_to_gpu_numa_node(device) if (make_backend is None and world > 1) else None
+        self.numa_node, self.numa_note = bind_to_gpu_numa_node(device) if (make_backend is None and world > 1) else (None, "single rank: not bound")
         self.mc = host_mod.MonteCarlo(argv, rank, world, allreduce=self._allreduce if world > 1 else None)
         self.ctx = None
         if make_backend is not None:
@@ -315,17 +325,90 @@ class Simulation:
         self.mc.close()
 
 
-def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder, deck_argv, ClockSampler):
+def run_resident_workload(argv, rank, world, local_rank, dist, validation, warmup, steps, env=None):
+    """A few whole cycles of one deck with the population resident on the device (cycleInit on the GPU, one tracking launch
+    per cycle, peer exchange between GPUs): the figure of merit of a secondary workload in bench.py's `workloads` block and
+    of the validation build.  Timing as for the headline `value`: one GPU -> CUDA events around the tracking kernel on its
+    own stream; several GPUs -> host clock between device synchronisations + barriers around the exchange, max over ranks.
+    Returns a dict (identical on every rank)."""
+    import os
+    import torch
+    saved = {}
+    for k, v in (env or {}).items():
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        sim = Simulation(argv, rank, world, device=local_rank, validation=validation, dist=dist if world > 1 else None, resident=True)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    dev = "cuda:%d" % local_rank
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    track_s = init_s = dev_track_s = 0.0
+    segments = 0
+    rows = []
+    launches0 = 0
+    for step in range(warmup + steps):
+        timed = step >= warmup
+        if step == warmup:
+            launches0 = sim.ctx.launch_count()
+        res = sim.mc.cycle_init_resident(sim.ctx)
+        barrier()
+        t0 = time.perf_counter()
+        sim.backend.device_ms = 0.0
+        if world == 1:
+            stats = sim.mc.cycle_tracking_resident(sim.ctx)
+            step_dev = stats.device_ms * 1e-3
+        else:
+            exchange_rounds(sim.backend, dist, rank, world)
+            torch.cuda.synchronize()
+            step_dev = sim.backend.device_ms * 1e-3
+        t1 = time.perf_counter()
+        if world > 1:
+            sim.mc.tracking_end_resident(sim.ctx)
+        row, flux = sim.mc.cycle_finalize()
+        rows.append([int(v) for v in row])
+        if timed:
+            track_s += step_dev if world == 1 else (t1 - t0)
+            dev_track_s += step_dev
+            init_s += res.device_ms * 1e-3
+            segments += int(row[BAL["num_segments"]])
+    launches = sim.ctx.launch_count() - launches0
+    t = torch.tensor([track_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    track_max = float(t.cpu()[0])
+    cum = sim.mc.cumulative_balance()
+    gains = int(cum[BAL["start"]] + cum[BAL["source"]] + cum[BAL["produce"]] + cum[BAL["split"]])
+    losses = int(cum[BAL["absorb"]] + cum[BAL["census"]] + cum[BAL["escape"]] + cum[BAL["rr"]] + cum[BAL["fission"]])
+    out = {"value": segments / track_max if track_max > 0 else 0.0, "unit": "segments/s", "steps": steps, "warmup": warmup,
+           "ms_per_step": 1e3 * track_max / max(steps, 1), "segments_per_step": segments // max(steps, 1),
+           "track_kernel_ms_rank0": 1e3 * dev_track_s / max(steps, 1), "cycle_init_kernel_ms_rank0": 1e3 * init_s / max(steps, 1),
+           "kernels": "validation" if validation else "fast", "gpu_launches": launches, "conserved": gains == losses,
+           "exchange": getattr(sim, "exchange", "none") if world > 1 else "none", "last_row": rows[-1],
+           "cells_rank0": int(sim.mc.image.n_cells), "groups": int(sim.mc.image.n_groups)}
+    sim.close()
+    return out
+
+
+def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder, deck_argv, ClockSampler, dist=None):
     """bench.py's B200 arm.  Times, per step, (a) the device-resident tracking (CUDA events inside qsb_track)
-    and (b) the host-buffer drop-in call, and returns totals reduced over ranks (max of times, sum of segments)."""
+    and (b) the host-buffer drop-in call, and returns totals reduced over ranks (max of times, sum of segments).
+    `dist`: the initialised torch.distributed module when world > 1 (bench.py owns the process group)."""
     import tempfile
     import torch
-    import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
     dev = "cuda:%d" % local_rank
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(dev))
     w = dict(workloads[args.workload])
     if args.scale != 1.0:
         k = args.scale ** (1.0 / 3.0)
@@ -351,6 +434,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
     launches0 = 0
     rows = []
     sampler = ClockSampler(local_rank)
+    peer_diag = {}
     for step in range(warmup + args.steps):
         timed = step >= warmup
         if step == warmup:
@@ -378,6 +462,10 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
         tb = time.perf_counter()
         if timed:
             sent_total += n_sent
+            if world > 1 and getattr(sim, "exchange", "") == "peer":
+                d = ctx.peer_diagnostics()
+                for k in ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "deposited"):
+                    peer_diag[k] = peer_diag.get(k, 0) + d[k]
         step_kernel_s = sim.backend.device_ms * 1e-3 if world == 1 else tb - ta
         if timed:
             device_s += sim.backend.device_ms * 1e-3
@@ -427,6 +515,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
             n_res = 20                                       # ~0.4 s of back-to-back cycles at benchmark size
             r_init = r_track = r_final = r_init_dev = r_track_dev = 0.0
             r_segments = 0
+            r_carried = 0
             r_launches0 = 0
             r_sampler = ClockSampler(local_rank, 50)           # back-to-back cycles keep the GPU busy: clocks under sustained load
             for k in range(1 + n_res):                       # the first one moves the census to the device: not timed
@@ -450,6 +539,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
                 t3 = time.perf_counter()
                 rows.append([int(v) for v in row])
                 if k >= 1:
+                    r_carried += int(res.n_start)
                     r_init += t1 - t0; r_track += t2 - t1; r_final += t3 - t2
                     r_init_dev += res.device_ms * 1e-3; r_track_dev += track_dev_ms * 1e-3
                     r_segments += int(row[BAL["num_segments"]])
@@ -463,6 +553,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
                                  "segments_per_s_whole_cycle": r_segments / r_total if r_total > 0 else 0.0,
                                  "segments_per_s_tracking": r_segments / r_track if r_track > 0 else 0.0,
                                  "cycle_init_kernel_ms_rank0": 1e3 * r_init_dev / n_res, "track_kernel_ms_rank0": 1e3 * r_track_dev / n_res,
+                                 "carried_per_cycle": r_carried / n_res,
                                  "gpu_launches": ctx.launch_count() - r_launches0,
                                  "pcie_bytes_per_cycle": BAL_COUNT * 8 + 8 + 48, "clocks": r_clocks,
                                  "note": "wall clock per rank around each stage, max over ranks; population resident in HBM, source + population "
@@ -511,7 +602,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
               "kernels": "fast" if args.fast else "validation", "timing": "inputs larger than L2 (vault %.0f MB, mesh %.0f MB per GPU); value: %s; e2e: wall clock around the "
               "drop-in call with host vaults" % (w["particles"] * 160 / 1e6, n ** 3 * 1.2e-3,
               "CUDA events on the tracking stream" if world == 1 else "host clock between device syncs + barriers around the exchange rounds, max over ranks"),
-              "scale": args.scale, "exchange": getattr(sim, "exchange", "none") if world > 1 else "none", "numa_node_rank0": sim.numa_node}
+              "scale": args.scale, "exchange": getattr(sim, "exchange", "none") if world > 1 else "none", "numa_node_rank0": sim.numa_node, "numa_note": sim.numa_note}
     out = {"segments_total": segments, "kernel_seconds_max": kernel_max, "e2e_seconds_max": e2e_max,
            "segments_rank0": segments / world, "kernel_seconds_rank0": kernel_s, "config": config, "clocks": clocks,
            "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
@@ -520,7 +611,18 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
                                           "cuda_events_on_kernel_stream": 1e3 * device_s / max(args.steps, 1),
                                           "host_clock_around_call": 1e3 * host_s / max(args.steps, 1)},
            "balance_check": {"gains": gains, "losses": losses, "conserved": gains == losses, "last_row": rows[-1]}}
-    sim.close()
     if world > 1:
-        dist.destroy_process_group()
+        # every rank's own numbers, so that the slowest rank and the termination tail are visible in the line (per timed step)
+        k = max(args.steps, 1)
+        mine = {"rank": rank, "kernel_ms": 1e3 * device_s / k, "host_clock_ms": 1e3 * host_s / k, "e2e_ms": 1e3 * e2e_s / k,
+                "boundary_particles_sent": sent_total // k}
+        if peer_diag:
+            mine.update(first_idle_ms=peer_diag["first_idle_ns"] * 1e-6 / k, done_ms=peer_diag["done_ns"] * 1e-6 / k,
+                        tail_ms=(peer_diag["done_ns"] - peer_diag["first_idle_ns"]) * 1e-6 / k,
+                        startup_wait_ms=peer_diag["startup_wait_ns"] * 1e-6 / k,
+                        send_mcycles_all_warps=peer_diag["send_cycles"] * 1e-6 / k, send_passes=peer_diag["send_calls"] // k)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        out["per_rank"] = gathered
+    sim.close()
     return out
