@@ -219,7 +219,7 @@ def reference_gpu_block(workload):
            "regs": 164, "stack_bytes": 872, "runs": {}}
     w = WORKLOADS[workload]
     cases = [("literal_deck_size", max(w["n"] // 4, 8), max(w["particles"] // 64, 10000), 5, 2, 300),
-             ("same_config", w["n"], w["particles"], 2, 1, 420)]
+             ("same_config", w["n"], w["particles"], 2, 1, 240)]
     for name, n, particles, steps, warm, limit in cases:
         try:
             r = run_reference(workload, steps, warm, n=n, particles=particles, threads=1, exe=exe, timeout=limit)

@@ -138,7 +138,7 @@ def test_fast_build_is_statistically_the_validation_build(tmp_path, name, n, cel
     deck = decks.write_deck(decks.derive(name, nSteps=cycles), str(tmp_path / (name + ".inp")))
     argv = ["-i", deck, "-X", n * cell_len, "-Y", n * cell_len, "-Z", n * cell_len, "-x", n, "-y", n, "-z", n, "-I", 1, "-J", 1, "-K", 1, "-n", particles]
     argv = [str(a) for a in argv]
-    cap = int(particles * 3.2) + (1 << 16)
+    cap = particles * 8 + (1 << 16)      # (3 + 2 nuBar) x the population, the driver's own sizing rule (secondaries append to the vault)
     rows_v, flux_v, ms_v = _run_build(argv, cycles, cap, True)
     rows_f, flux_f, ms_f = _run_build(argv, cycles, cap, False)
     bad = ksigma_violations(rows_v, rows_f)
