@@ -211,7 +211,10 @@ typedef struct qsb_ctx qsb_ctx;
 typedef struct qsb_options {
     int32_t  validation;        /* 1: --fmad=false kernels + strict log/sin/cos (bit-exact vs oracle);
                                    0: fast build (FMA contraction of the same source)                  */
-    int32_t  tracking_mode;     /* bit 0 reserved (0: history-based persistent kernel); bit 1 (value 2): run the
+    int32_t  tracking_mode;     /* bit 0: 0 = event-based kernel (the default: particles in shared memory, every warp runs
+                                   batches of ONE event type over its own slots), 1 = history-based persistent kernel (one
+                                   lane = one history in registers); same results bit for bit; QSB_TRACKING=history|event
+                                   in the environment overrides.  bit 1 (value 2): run the
                                    filtered and the full nearest-facet search side by side and count mismatches;
                                    bit 2 (value 4): likewise for the direct reaction selection vs the subtraction chain */
     uint64_t particle_capacity; /* SoA slots per vault; 0 = 1 << 20 (callers size it: nParticles x (3 + 2 nuBar)) */

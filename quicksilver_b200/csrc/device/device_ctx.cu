@@ -260,6 +260,8 @@ struct qsb_ctx
     uint32_t epoch = 0;
     uint64_t launches = 0;
     int grid = 0, block = 128, regs = 0, blocks_per_sm = 0;
+    bool event_mode = false;                    // tracking_mode bit 0: the event-based kernel (track_event_kernels.cu)
+    int evt_smem = 0, evt_slots = 0;
     bool in_cycle = false;
     std::string error;
 };
@@ -462,6 +464,53 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
             }
             im.compact = compact ? 1 : 0;
             im.cells = devUpload(recs.data(), nc, c->owned);
+            // computed-neighbour path (DevImage::brick): the three strides are read off the first on-processor transit of each
+            // axis and then checked on EVERY transit face of every cell; any exception (several domains per rank, a domain that
+            // is not one lexicographically numbered brick) leaves the kernels on the adjacency records
+            {
+                int stride[3] = { 0, 0, 0 };
+                bool ok = nm <= 255;
+                for (size_t cidx = 0; cidx < nc && ok; ++cidx)
+                    for (int face = 0; face < 6; ++face)
+                    {
+                        if ((image->face_event[cidx * 6 + face] & 0xf) != QSB_ADJ_TRANSIT_ON) continue;
+                        const long long d = (long long)image->face_adj_cell[cidx * 6 + face] - (long long)cidx;
+                        const long long want = (face & 1) ? -d : d;            // faces 0,2,4 look towards +x,+y,+z, faces 1,3,5 towards -x,-y,-z
+                        const int ax = face >> 1;
+                        if (stride[ax] == 0 && want > 0 && want < (1ll << 30)) stride[ax] = (int)want;
+                        if (want != stride[ax] || want <= 0) { ok = false; break; }
+                        // the neighbour's grid position must be this cell's, one step along the axis (the kernel derives it)
+                        const int g0 = image->cell_gid[cidx], g1 = image->cell_gid[image->face_adj_cell[cidx * 6 + face]];
+                        const int step = ax == 0 ? 1 : (ax == 1 ? nx : nx * ny);
+                        if (g1 - g0 != ((face & 1) ? -step : step)) { ok = false; break; }
+                    }
+                std::vector<uint32_t> info(nc);
+                for (size_t cidx = 0; cidx < nc; ++cidx) info[cidx] = (recs[cidx].events & 0xffffffu) | ((uint32_t)recs[cidx].material << 24);
+                im.cell_info = devUpload(info.data(), nc, c->owned);
+                im.brick = (ok && std::getenv("QSB_NO_BRICK") == nullptr) ? 1 : 0;
+                for (int k = 0; k < 3; ++k) im.brick_stride[k] = stride[k];
+            }
+            // compact reaction table: isotope 0's rows only, when every material's isotopes share one table
+            {
+                bool all_periodic = true;
+                int nr = 0;
+                for (size_t m = 0; m < nm; ++m)
+                {
+                    if (!image->mat_periodic[m] || image->mat_n_reactions[m] > 9) all_periodic = false;
+                    nr = std::max(nr, (int)image->mat_n_reactions[m]);
+                }
+                im.xs_compact = nullptr; im.compact_react = 0;
+                if (all_periodic && nr > 0 && std::getenv("QSB_NO_COMPACT_XS") == nullptr)
+                {
+                    std::vector<double> compactTable(nm * ng * (size_t)nr, 0.0);
+                    for (size_t m = 0; m < nm; ++m)
+                        for (size_t g = 0; g < ng; ++g)
+                            for (int k = 0; k < image->mat_n_reactions[m]; ++k)
+                                compactTable[(m * ng + g) * nr + k] = image->xs_react[(m * ng + g) * mr + k];
+                    im.xs_compact = devUpload(compactTable.data(), compactTable.size(), c->owned);
+                    im.compact_react = nr;
+                }
+            }
             std::vector<double2> pairs(nm * ng);
             for (size_t i = 0; i < nm * ng; ++i) { pairs[i].x = image->xs_total[i]; pairs[i].y = 1.0 / image->xs_total[i]; }
             im.xs_pair = devUpload(pairs.data(), nm * ng, c->owned);
@@ -509,8 +558,21 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         // the kernel is compiled with __launch_bounds__(128) and uses full-mask warp intrinsics throughout
         if (c->block < 32 || c->block > 128 || (c->block & 31) != 0)
             throw CudaFailure{ "qsb_options.threads_per_block must be a multiple of 32 between 32 and 128" };
-        if (c->opt.validation) track_kernel_attributes_validation(&c->regs, &c->blocks_per_sm, c->block);
-        else                   track_kernel_attributes_fast(&c->regs, &c->blocks_per_sm, c->block);
+        // which tracking kernel: tracking_mode bit 0 (0: the default, event-based -- measured 15-20 % faster, DESIGN.md
+        // section 5; 1: history-based); QSB_TRACKING=history|event overrides (A/B measurements: bench.py)
+        c->event_mode = (c->opt.tracking_mode & 1) == 0;
+        if (const char* e = std::getenv("QSB_TRACKING"))
+        {
+            if (std::strcmp(e, "event") == 0) c->event_mode = true;
+            else if (std::strcmp(e, "history") == 0) c->event_mode = false;
+        }
+        if (c->event_mode)
+        {
+            if (c->opt.validation) track_event_kernel_attributes_validation(&c->regs, &c->blocks_per_sm, &c->block, &c->evt_smem, &c->evt_slots);
+            else                   track_event_kernel_attributes_fast(&c->regs, &c->blocks_per_sm, &c->block, &c->evt_smem, &c->evt_slots);
+        }
+        else if (c->opt.validation) track_kernel_attributes_validation(&c->regs, &c->blocks_per_sm, c->block);
+        else                        track_kernel_attributes_fast(&c->regs, &c->blocks_per_sm, c->block);
         check(cudaGetLastError(), "kernel attributes (is the sm_100a image loadable on this device?)");
         if (c->blocks_per_sm < 1) throw CudaFailure{ "tracking kernel cannot be resident on this device" };
         if (c->opt.blocks_per_sm > 0) c->blocks_per_sm = std::min(c->blocks_per_sm, c->opt.blocks_per_sm);
@@ -969,8 +1031,13 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         QSB_CUDA(cudaEventRecord(c->ev0, c->stream));
         if (c->h_ctl->inflight > 0 || c->peer_on)        // peer mode: every rank takes part in every launch (arrivals, termination)
         {
-            if (c->opt.validation) launch_track_validation(a, c->grid, c->block, c->stream);
-            else                   launch_track_fast(a, c->grid, c->block, c->stream);
+            if (c->event_mode)
+            {
+                if (c->opt.validation) launch_track_event_validation(a, c->grid, c->stream);
+                else                   launch_track_event_fast(a, c->grid, c->stream);
+            }
+            else if (c->opt.validation) launch_track_validation(a, c->grid, c->block, c->stream);
+            else                        launch_track_fast(a, c->grid, c->block, c->stream);
             QSB_CUDA(cudaGetLastError());
             ++n_launch; c->launches++;
         }
@@ -1032,6 +1099,8 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         if (c->h_ctl->overflow)
         {
             char msg[160];
+            if (c->h_ctl->overflow & 8u)
+            { c->error = "the tracking kernel's watchdog expired with histories still in flight (internal error)"; return (int)QSB_ERR_INTERNAL; }
             std::snprintf(msg, sizeof msg, "fixed-capacity storage overflowed (mask %u: 1 processing vault, 2 census vault, 4 send slab); "
                           "raise qsb_options.particle_capacity / send_capacity", c->h_ctl->overflow);
             c->error = msg;

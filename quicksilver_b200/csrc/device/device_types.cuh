@@ -56,6 +56,18 @@ struct DevImage
     const int*     mat_n_react;     // [n_materials]
     const uint8_t* mat_react_type;  // [n_materials*max_react]
     const uint8_t* mat_periodic;    // [n_materials]
+    // ---- derived, optional fast paths (set up and VERIFIED against the arrays above by qsb_create) ----
+    // brick: every on-processor transit leads to cell + {+sx, -sx, +sy, -sy, +sz, -sz}[face] (one lexicographically numbered
+    // brick per rank): the neighbour is computed instead of read from the cell record, and what the tracking loop needs of
+    // the new cell -- face events and material, one word -- comes from a 4-byte-per-cell array (1 MB at 64^3 cells instead
+    // of a 16 MB record array); its grid indices follow from the old ones.
+    int brick;                      // 1: the computed-neighbour path is valid for this image
+    int brick_stride[3];            // sx, sy, sz
+    const uint32_t* cell_info;      // [n_cells] events (6 x 4 bits) | material << 24
+    // compact reaction table: when every material is periodic (one reaction table shared by its isotopes) only the first
+    // isotope's rows are ever read: [n_materials][n_groups][compact_react] instead of rows of max_react doubles
+    const double*  xs_compact;      // nullptr: not available
+    int compact_react;
 };
 
 // SoA particle vault: one array per MC_Base_Particle field (src/MC_Base_Particle.hh:75-92), cell is the
@@ -232,6 +244,11 @@ void launch_track_validation(const TrackArgs& a, int grid, int block, cudaStream
 void launch_track_fast(const TrackArgs& a, int grid, int block, cudaStream_t s);
 void track_kernel_attributes_validation(int* regs, int* max_blocks_per_sm, int block);
 void track_kernel_attributes_fast(int* regs, int* max_blocks_per_sm, int block);
+// the event-based kernels (track_event_kernels.cu; tracking_mode bit 0): block shape and shared memory are compile-time
+void launch_track_event_validation(const TrackArgs& a, int grid, cudaStream_t s);
+void launch_track_event_fast(const TrackArgs& a, int grid, cudaStream_t s);
+void track_event_kernel_attributes_validation(int* regs, int* max_blocks_per_sm, int* threads, int* smem_bytes, int* slots);
+void track_event_kernel_attributes_fast(int* regs, int* max_blocks_per_sm, int* threads, int* smem_bytes, int* slots);
 
 } // namespace qsb
 #endif

@@ -1,0 +1,721 @@
+// track_event_kernels.cu -- event-based cycle tracking (the default; tracking_mode bit 0 = 1 selects the history kernel).
+//
+// The history-based kernel (track_kernels.cu) keeps one history per lane in registers and regroups lanes inside a warp by
+// what they need next; ncu puts it at 18.6 of 32 lanes per instruction with 160 registers of live particle state + event
+// code.  Here the particles live in SHARED MEMORY -- structure of arrays over slots, ~175 bytes per particle, kWq slots
+// owned by every WARP -- and a warp runs batches of ONE event type over its own slots:
+//
+//   LOAD       take a ticket of the processing-vault queue, redeem it when the slot is written, particle -> shared memory
+//   SEGMENT    MC_Segment_Outcome + (for a facet crossing) MC_Facet_Crossing_Event         src/MC_Segment_Outcome.cc, ...
+//   COLLISION  CollisionEvent (+ the outgoing trajectory of freshly loaded fission secondaries)   src/CollisionEvent.cc
+//   CENSUS     store the record in the census vault                                               src/CycleTracking.cc:93-103
+//   SEND       a particle that left the rank's domain: NVLink deposit on the peer / send slab     src/MC_Facet_Crossing_Event.cc:49-67
+//
+// A slot's state byte says which event it waits for.  Per iteration the warp picks one event type (one with >= 32 waiting
+// slots if there is one: collisions first, they are the longest), gathers up to 32 such slots into a list with ballots,
+// loads exactly the fields that event reads, runs the SAME device functions as the history kernel (track_physics.cuh: the
+// arithmetic, and therefore every bit of every result, is shared), stores the fields the event may have changed and sets
+// the slots' next states.  With 96 slots per warp every SEGMENT / COLLISION batch is full (31.2 of 32 lanes enter a segment
+// batch, ncu); no particle state is live in registers across events; nothing is shared between warps -- no block barrier, no
+// shared-memory atomics (a first version with block-wide queues and one __syncthreads per phase lost 19 % of its cycles at
+// the barrier and ran 0.85x the history kernel; this one runs 1.17x, profiles/r02_event_kernel_shapes.txt).
+//
+// Everything outside the warp is the history kernel's: the ticket queue over the processing vault (fission secondaries
+// are appended to the vault and picked up by whichever warp redeems their ticket), the global in-flight counter, the
+// census append, the peer deposits and the termination protocol.  Results are independent of the scheduling: a
+// history's random numbers come from its own stream and tallies are sums (tests: bit-identical census and balance).
+#include "track_physics.cuh"
+
+namespace qsb {
+namespace {
+
+
+
+// a block's particle slots: structure of arrays over N slots
+template <int N>
+struct SlotStore
+{
+    double x[N], y[N], z[N], alpha[N], beta[N], gamma[N];
+    double energy[N], weight[N], ttc[N], age[N], nmfp[N], nseg[N], speed[N];
+#if QSB_VALIDATION
+    double vx[N], vy[N], vz[N];
+#endif
+    unsigned long long seed[N];
+    unsigned long long id[N];              // LOAD state: the slot's ticket (kNoTicket: none yet)
+    uint2 head01[N];                       // CellRec words 0-1: ix | iy << 16, iz | material << 16
+    unsigned events[N];                    // CellRec word 2: 4 bits per face
+    int cell[N];
+    int num_collisions[N], breed[N], species[N];
+    unsigned short group[N];
+    unsigned char facet[N], last_event[N], flags[N];
+};
+
+
+// the balance counters a warp keeps (Counters of the history kernel), see the kernel's epilogue
+enum { kTalSegments = 0, kTalCollisions, kTalAbsorbs, kTalFissions, kTalProduced, kTalEscapes, kTalCensus, kTalScatters, kTalLookups, kTalSlow, kTalMismatch };
+
+template <class Store>
+__device__ __forceinline__ void load_head(const Store& s, unsigned slot, Particle& p)
+{
+    const uint2 h = s.head01[slot];
+    p.head = make_uint4(h.x, h.y, s.events[slot], 0u);
+}
+template <class Store>
+__device__ __forceinline__ void store_head(Store& s, unsigned slot, const Particle& p)
+{
+    s.head01[slot] = make_uint2(p.head.x, p.head.y);
+    s.events[slot] = p.head.z;
+}
+
+// every field of a particle, registers <-> slot (LOAD writes, CENSUS / SEND read)
+template <class Store>
+__device__ __forceinline__ void store_all(Store& s, unsigned slot, const Particle& p)
+{
+    s.x[slot] = p.x; s.y[slot] = p.y; s.z[slot] = p.z;
+    s.alpha[slot] = p.alpha; s.beta[slot] = p.beta; s.gamma[slot] = p.gamma;
+    s.energy[slot] = p.energy; s.weight[slot] = p.weight; s.ttc[slot] = p.ttc; s.age[slot] = p.age;
+    s.nmfp[slot] = p.nmfp; s.nseg[slot] = p.nseg; s.speed[slot] = p.speed;
+#if QSB_VALIDATION
+    s.vx[slot] = p.vx; s.vy[slot] = p.vy; s.vz[slot] = p.vz;
+#endif
+    s.seed[slot] = p.seed; s.id[slot] = p.id;
+    store_head(s, slot, p);
+    s.cell[slot] = p.cell;
+    s.num_collisions[slot] = p.num_collisions; s.breed[slot] = p.breed; s.species[slot] = p.species;
+    s.group[slot] = (unsigned short)p.group;
+    s.facet[slot] = (unsigned char)p.facet; s.last_event[slot] = (unsigned char)p.last_event;
+}
+template <class Store>
+__device__ __forceinline__ void load_all(const Store& s, unsigned slot, Particle& p)
+{
+    p.x = s.x[slot]; p.y = s.y[slot]; p.z = s.z[slot];
+    p.alpha = s.alpha[slot]; p.beta = s.beta[slot]; p.gamma = s.gamma[slot];
+    p.energy = s.energy[slot]; p.weight = s.weight[slot]; p.ttc = s.ttc[slot]; p.age = s.age[slot];
+    p.nmfp = s.nmfp[slot]; p.nseg = s.nseg[slot]; p.speed = s.speed[slot];
+#if QSB_VALIDATION
+    p.vx = s.vx[slot]; p.vy = s.vy[slot]; p.vz = s.vz[slot];
+#else
+    p.vx = p.vy = p.vz = 0.0;
+#endif
+    p.seed = s.seed[slot]; p.id = s.id[slot];
+    load_head(s, slot, p);
+    p.cell = s.cell[slot];
+    p.num_collisions = s.num_collisions[slot]; p.breed = s.breed[slot]; p.species = s.species[slot];
+    p.group = s.group[slot];
+    p.facet = s.facet[slot]; p.last_event = s.last_event[slot];
+    p.total_xs = 0.0;
+}
+
+// shape (csrc/Makefile: EVT_DEFS): particle slots per warp, warps per block, resident blocks per SM
+#ifndef QSB_WQ_SLOTS_PER_WARP
+#define QSB_WQ_SLOTS_PER_WARP 96
+#endif
+#ifndef QSB_WQ_WARPS
+#define QSB_WQ_WARPS 4
+#endif
+#ifndef QSB_WQ_MIN_BLOCKS
+#define QSB_WQ_MIN_BLOCKS 3
+#endif
+constexpr int kWq = QSB_WQ_SLOTS_PER_WARP;          // slots per warp
+constexpr int kWqK = (kWq + 31) / 32;               // ... per lane of bookkeeping
+constexpr int kWqWarps = QSB_WQ_WARPS;
+constexpr int kWqThreads = 32 * kWqWarps;
+constexpr int kWqSlots = kWq * kWqWarps;
+static_assert(kWq % 4 == 0 && kWq >= 32 && kWq <= 256, "a warp's slots: at least a batch, slot numbers fit a byte");
+
+enum { kStLoad = 0, kStSegment, kStCollision, kStTail, kStCensus, kStSend };
+
+// A warp's scheduler state lives in shared memory, not in registers: the event code in between is where the register
+// budget goes, and anything that stays live across it is spilled to local memory (measured: the spilled per-thread balance
+// counters and slot counts alone were 15 % of all stall samples).  Everybody reads it at the top of an iteration (one
+// broadcast load each), lane 0 updates it at the end of a batch.
+enum { kNSeg = 0, kNCol, kNCen, kNSnd, kNLoad, kNWait, kNCounts };
+struct WqWarpState
+{
+    int n[kNCounts];                // slots per state; kNWait: tickets held that could not be redeemed at the last LOAD
+    unsigned retired;               // histories ended, not yet subtracted from the global in-flight count
+    unsigned backoff;
+    unsigned has_pub;               // some lane wrote fission secondaries in the last collision batch (pub_first / pub_n): publish them
+    unsigned pad;
+    unsigned tally[12];             // the warp's balance counters (kTal*), flushed once at kernel end
+    unsigned long long in_seen;     // host-buffer streaming: last value of ctl->in_ready the warp has seen
+    unsigned long long t_start;
+};
+
+struct WqShared : SlotStore<kWqSlots>
+{
+    unsigned char state[kWqSlots];                  // what each slot waits for (kSt*)
+    unsigned char list[kWqWarps][kWq];              // the warp's gather list: slots (warp-relative) of the batch being formed
+    WqWarpState w[kWqWarps];
+    unsigned long long pub_first[kWqThreads];       // per thread: first vault slot / number of the secondaries it wrote last
+    unsigned pub_n[kWqThreads];
+    PeerLaunch launch[kMaxPeers];
+};
+
+// gather the warp's slots whose state satisfies `pred` into its list (slot order); returns how many
+template <class Pred>
+__device__ __forceinline__ unsigned wq_gather(WqShared& s, unsigned warp, unsigned lane, Pred pred)
+{
+    unsigned total = 0;
+#pragma unroll
+    for (int k = 0; k < kWqK; ++k)
+    {
+        const bool hit = (kWq % 32 == 0 || 32 * k + (int)lane < kWq) && pred(s.state[warp * kWq + 32 * k + lane]);
+        const unsigned m = __ballot_sync(kFullMask, hit);
+        if (hit) s.list[warp][total + __popc(m & ((1u << lane) - 1u))] = (unsigned char)(32 * k + lane);
+        total += __popc(m);
+    }
+    __syncwarp();
+    return total;
+}
+
+// The events a history meets once (LOAD, CENSUS) or rarely (SEND) are separate functions: the hot loop -- choose, SEGMENT,
+// COLLISION -- stays small enough for the instruction caches (the warp-state samples of the history kernel and of the first
+// event kernels showed 10-17 % of cycles waiting for instructions).
+
+// LOAD: every slot of the warp without a particle; empty ones take a ticket (one global atomic per batch of 32), tickets
+// are redeemed once the vault slot they name has been written -- the history kernel's protocol (its service phase).
+struct WqLoaded { int to_segment, to_tail, waiting; };
+__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take)
+{
+    const unsigned base = warp * kWq;
+    unsigned long long in_seen = s.w[warp].in_seen;
+    const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStLoad; });
+    WqLoaded out = { 0, 0, 0 };
+    for (unsigned first = 0; first < total; first += 32u)
+    {
+        const bool active = first + lane < total;
+        const unsigned slot = base + (active ? s.list[warp][first + lane] : 0u);
+        unsigned long long ticket = active ? s.id[slot] : kNoTicket;
+        const bool want = active && ticket == kNoTicket && may_take;
+        const unsigned want_mask = __ballot_sync(kFullMask, want);
+        if (want_mask)
+        {
+            unsigned long long tb = 0;
+            const unsigned leader = __ffs(want_mask) - 1;
+            if (lane == leader) tb = atomicAdd(&a.ctl->head, (unsigned long long)__popc(want_mask));
+            tb = __shfl_sync(kFullMask, tb, leader);
+            if (want) ticket = tb + __popc(want_mask & ((1u << lane) - 1u));
+        }
+        bool ready = false;
+        if (active && ticket != kNoTicket)
+        {
+            if (ticket < a.n_in)
+            {
+                if (ticket >= in_seen)
+                    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(in_seen) : "l"(&a.ctl->in_ready) : "memory");
+                ready = ticket < in_seen;
+            }
+            else if (ticket - a.n_in < a.proc.capacity)
+            {
+                const unsigned long long vslot = ticket - a.n_in;
+                ready = vslot < a.ready_prefix;
+                if (!ready)
+                {
+                    uint32_t flag;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + vslot) : "memory");
+                    ready = flag == a.epoch;
+                    if (__builtin_expect(flag == (a.epoch | kArrivalBit), 0)) ready = deposit_complete(a.proc, vslot, a.epoch);
+                }
+            }
+        }
+        int state = kStateIdle;
+        if (ready)
+        {
+            Particle p;
+            if (ticket < a.n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
+            else state = load_particle(a, ticket - a.n_in, p);
+            store_all(s, slot, p);
+            s.state[slot] = (unsigned char)(state == kStateTail ? kStTail : kStSegment);
+        }
+        else if (active) s.id[slot] = ticket;
+        out.to_segment += __popc(__ballot_sync(kFullMask, state == kStateSegment));
+        out.to_tail += __popc(__ballot_sync(kFullMask, state == kStateTail));
+        out.waiting += __popc(__ballot_sync(kFullMask, active && !ready && ticket != kNoTicket));
+    }
+    // keep the highest DMA front any lane has seen
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(kFullMask, in_seen, d); in_seen = o > in_seen ? o : in_seen; }
+    if (lane == 0) s.w[warp].in_seen = in_seen;
+    return out;
+}
+
+// CENSUS: up to 32 histories that reached census; their records go to the census vault (or the streamed record buffer)
+__device__ __noinline__ int wq_census(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
+{
+    const unsigned base = warp * kWq;
+    const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStCensus; });
+    const bool active = lane < total;
+    const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
+    Particle p;
+    if (active) load_all(s, slot, p);
+    const unsigned mask = __ballot_sync(kFullMask, active);
+    unsigned long long cbase = 0;
+    unsigned count = 0;
+    if (lane == 0)
+    {
+        count = __popc(mask);
+        cbase = atomicAdd(&a.ctl->census_count, (unsigned long long)count);
+    }
+    census_flush(a, p, active, lane, cbase, count, 0u, lane);
+    if (active) { s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad; }
+    return __popc(mask);
+}
+
+// SEND: up to 32 particles whose facet crossing leaves this rank's domain.  NCCL-rounds mode: packed into the per-peer slab
+// (facet_crossing_event's own code path).  Peer mode: deposited straight into the neighbour GPU's processing vault over
+// NVLink; the remote counters are raised once per (batch, destination) instead of once per particle, in the order the
+// termination test relies on (peer's `sent` and `inflight` before the record is stored and the history retired here; peer's
+// `received` after its `inflight`), see send_advance in track_physics.cuh.
+template <int kPeer>
+__device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
+{
+    const unsigned base = warp * kWq;
+    const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStSend; });
+    const bool active = lane < total;
+    const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
+    Particle p;
+    if (active) load_all(s, slot, p);
+    if (!(kPeer && a.peer_mode))
+    {
+        Counters unused = {};
+        if (active) facet_crossing_event(a, p, unused);     // TRANSIT_OFF: writes the exchange record into the per-peer slab
+    }
+    else if (kPeer)
+    {
+        const DevImage& im = a.im;
+        int rank = -1;
+        size_t k = 0;
+        if (active) { k = (size_t)p.cell * 6 + (p.facet >> 2); rank = __ldg(im.face_nbr_rank + k); }
+        unsigned todo = __ballot_sync(kFullMask, active);
+        while (todo)
+        {
+            const unsigned head_lane = __ffs(todo) - 1;
+            const int dest = __shfl_sync(kFullMask, rank, head_lane);
+            const unsigned group = __ballot_sync(kFullMask, active && rank == dest);
+            const unsigned n = __popc(group);
+            unsigned long long ticket0 = 0, dep = 0, dep2 = 0;
+            PeerControl* pc = peer_control(a, dest);
+            if (lane == head_lane)
+            {
+                atomicAdd(&a.ctl->send_count[dest], (unsigned long long)n);          // statistics only
+                dep = atomicAdd_system(&pc->sent, (unsigned long long)n);
+                dep2 = atomicAdd_system(&pc->inflight, (unsigned long long)n);
+                ticket0 = atomicAdd_system(&pc->tail, (unsigned long long)n);
+                asm volatile("" :: "l"(dep), "l"(dep2) : "memory");                 // performed: their values are here
+            }
+            ticket0 = __shfl_sync(kFullMask, ticket0, head_lane);
+            if (active && rank == dest)
+            {
+                const unsigned long long vslot = ticket0 + __popc(group & ((1u << lane) - 1u)) - s.launch[dest].n_in;
+                if (vslot >= a.proc.capacity)
+                {
+                    st_release_sys(&pc->overflow, a.peer_epoch);                     // the peer's host reports it; the particle is dropped
+                    atomicAdd_system(&pc->inflight, 0ull - 1ull);
+                }
+                else
+                    store_deposit(vault_view(a.peer_base[dest], a.proc.capacity), vslot, p, __ldg(im.face_adj_cell + k), s.launch[dest].vault_epoch);
+            }
+            __syncwarp();
+            if (lane == head_lane)
+                asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&pc->received), "l"((unsigned long long)n) : "memory");
+            todo &= ~group;
+        }
+    }
+    if (active) { s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad; }
+    return (int)min(total, 32u);
+}
+
+template <int kDummy, int kPeer>
+__global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_kernel(const __grid_constant__ TrackArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WqShared& s = *reinterpret_cast<WqShared*>(smem_raw);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned base = warp * kWq;
+
+    if (kPeer && a.peer_mode)
+    {
+        if (blockIdx.x == 0)                                    // the service block: global termination, tracks nothing
+        {
+            if (threadIdx.x < 32u)
+            {
+                const PeerControl* pc = peer_control(a, (int)min(threadIdx.x, (unsigned)(a.im.n_ranks - 1)));
+                const unsigned long long t0 = global_timer_ns();
+                while (ld_acquire_sys(&pc->epoch) != a.peer_epoch && global_timer_ns() - t0 < a.watchdog_ns) __nanosleep(500);
+                if (threadIdx.x == 0) peer_control(a, a.my_rank)->startup_wait_ns = global_timer_ns() - t0;
+                __syncwarp();
+                peer_service_loop(a, lane);
+            }
+            return;
+        }
+        if ((int)threadIdx.x < a.im.n_ranks)
+        {
+            const PeerControl* pc = peer_control(a, (int)threadIdx.x);
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(&pc->epoch) != a.peer_epoch && global_timer_ns() - t0 < a.watchdog_ns) __nanosleep(500);
+            s.launch[threadIdx.x].n_in = ld_relaxed_sys(&pc->n_in);
+            s.launch[threadIdx.x].vault_epoch = ld_relaxed_sys(&pc->vault_epoch);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int k = 0; k < kWqK; ++k)
+        if (kWq % 32 == 0 || 32 * k + (int)lane < kWq) { s.state[base + 32 * k + lane] = (unsigned char)kStLoad; s.id[base + 32 * k + lane] = kNoTicket; }
+    s.pub_n[threadIdx.x] = 0u;
+    if (lane == 0)
+    {
+        WqWarpState& w0 = s.w[warp];
+        for (int k = 0; k < kNCounts; ++k) w0.n[k] = 0;
+        w0.n[kNLoad] = kWq;
+        w0.retired = 0u; w0.backoff = 64u; w0.has_pub = 0u; w0.pad = 0u;
+        for (int k = 0; k < 12; ++k) w0.tally[k] = 0u;
+        w0.in_seen = 0ull; w0.t_start = global_timer_ns();
+    }
+
+    for (;;)
+    {
+        __syncwarp();
+        WqWarpState& w = s.w[warp];
+        const int n_seg = w.n[kNSeg], n_col = w.n[kNCol], n_cen = w.n[kNCen], n_snd = w.n[kNSnd], n_load = w.n[kNLoad], n_wait = w.n[kNWait];
+        const unsigned has_pub = w.has_pub;
+        __syncwarp();                                   // everybody has read the state before lane 0 may change it
+        if (has_pub)
+        {
+            const unsigned pub_n = s.pub_n[threadIdx.x];
+            publish_children(a, s.pub_first[threadIdx.x], pub_n, a.epoch);
+            s.pub_n[threadIdx.x] = 0u;
+            if (lane == 0) w.has_pub = 0u;
+        }
+
+        // ---- which event next ----
+        const bool may_take = n_wait < 32;              // tickets are handed out in order: holding unredeemable ones means the queue's tail is reached
+        const int n_fill = may_take ? n_load - n_wait : 0;
+        int type;
+        if (n_col >= 32) type = kStCollision;
+        else if (n_seg >= 32) type = kStSegment;
+        else if (n_fill >= 16) type = kStLoad;
+        else if (n_cen >= 32) type = kStCensus;
+        else if (n_snd >= 32) type = kStSend;
+        else if (n_fill > 0) type = kStLoad;
+        else
+        {
+            type = kStSegment; int best = n_seg;
+            if (n_col > best) { best = n_col; type = kStCollision; }
+            if (n_cen > best) { best = n_cen; type = kStCensus; }
+            if (n_snd > best) { best = n_snd; type = kStSend; }
+            if (best == 0)
+            {
+                // only tickets that cannot be redeemed yet: the warp is idle.  The cycle is over when no history is queued or
+                // running anywhere on this GPU -- or, in peer mode, anywhere on any GPU (the service warp's verdict)
+                unsigned done = 0u, backoff = 64u;
+                if (lane == 0)
+                {
+                    if (w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
+                    if (!(kPeer && a.peer_mode))
+                    {
+                        done = atomicAdd(a.inflight, 0ull) == 0ull ? 1u : 0u;
+                        if (!done && global_timer_ns() - w.t_start > (a.watchdog_ns ? a.watchdog_ns : 20000000000ull))
+                        { atomicOr(&a.ctl->overflow, 8u); done = 1u; }       // never hang the device: give up, loudly
+                    }
+                    else
+                    {
+                        const PeerControl* me = peer_control(a, a.my_rank);
+                        const unsigned d = *((volatile const unsigned int*)&me->done), ab = *((volatile const unsigned int*)&me->abort);
+                        done = (d == a.peer_epoch || ab == a.peer_epoch) ? 1u : 0u;
+                    }
+                    backoff = w.backoff;
+                    if (backoff < 2048u) w.backoff = backoff * 2u;
+                }
+                if (__shfl_sync(kFullMask, done, 0)) break;
+                __nanosleep(__shfl_sync(kFullMask, backoff, 0));
+                type = kStLoad;
+            }
+        }
+
+        if (type == kStLoad)
+        {
+            if (lane == 0 && w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
+            const WqLoaded got = wq_load(a, s, warp, lane, may_take);
+            if (lane == 0)
+            {
+                w.n[kNSeg] += got.to_segment; w.n[kNCol] += got.to_tail; w.n[kNLoad] -= got.to_segment + got.to_tail;
+                w.n[kNWait] = got.waiting;
+                if (got.to_segment | got.to_tail) w.backoff = 64u;
+            }
+            continue;
+        }
+
+        if (type == kStSegment)
+        {
+            const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStSegment; });
+            const bool active = lane < total;
+            const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
+            int next = -1;
+#if QSB_VALIDATION
+            unsigned slow = 0u, mismatch = 0u;
+#endif
+            if (active)
+            {
+                Counters c = {};
+                Particle p;
+                p.x = s.x[slot]; p.y = s.y[slot]; p.z = s.z[slot];
+                p.alpha = s.alpha[slot]; p.beta = s.beta[slot]; p.gamma = s.gamma[slot];
+                p.weight = s.weight[slot]; p.ttc = s.ttc[slot]; p.age = s.age[slot];
+                p.nmfp = s.nmfp[slot]; p.nseg = s.nseg[slot]; p.speed = s.speed[slot];
+#if QSB_VALIDATION
+                p.vx = s.vx[slot]; p.vy = s.vy[slot]; p.vz = s.vz[slot];
+#endif
+                p.seed = s.seed[slot];
+                load_head(s, slot, p);
+                p.cell = s.cell[slot];
+                p.group = s.group[slot];
+                p.facet = 0; p.last_event = 0; p.species = 0; p.total_xs = 0.0;
+
+                const int outcome = segment_outcome(a, p, c);
+                p.nseg += 1.;
+                if (outcome == 0) next = kStCollision;
+                else if (outcome == 1)
+                {
+                    if (face_event(p.head, p.facet >> 2) == QSB_ADJ_TRANSIT_OFF)
+                    {
+                        p.last_event = QSB_EV_COMMUNICATION;        // leaves the rank's domain: shipped by its own event (SEND), which needs every field
+                        next = kStSend;
+                    }
+                    else next = facet_crossing_event(a, p, c) == 1 ? kStSegment : kStLoad;      // kStLoad: escaped, the slot is free
+                }
+                else next = kStCensus;
+#if QSB_VALIDATION
+                slow = c.slow; mismatch = c.mismatch;
+#endif
+
+                s.x[slot] = p.x; s.y[slot] = p.y; s.z[slot] = p.z;
+                s.ttc[slot] = p.ttc; s.age[slot] = p.age; s.nmfp[slot] = p.nmfp; s.nseg[slot] = p.nseg;
+                s.seed[slot] = p.seed;
+                s.last_event[slot] = (unsigned char)p.last_event;
+                if (outcome == 1)
+                {
+                    s.facet[slot] = (unsigned char)p.facet;
+                    s.cell[slot] = p.cell;
+                    store_head(s, slot, p);
+                    s.alpha[slot] = p.alpha; s.beta[slot] = p.beta; s.gamma[slot] = p.gamma;       // reflection
+#if QSB_VALIDATION
+                    s.vx[slot] = p.vx; s.vy[slot] = p.vy; s.vz[slot] = p.vz; s.speed[slot] = p.speed;
+#endif
+                }
+                if (next == kStLoad) s.id[slot] = kNoTicket;
+                s.state[slot] = (unsigned char)next;
+            }
+            // where the batch went: the warp's slot counts and its balance tallies (every active lane advanced one segment;
+            // a history that left SEGMENT for LOAD escaped, src/MC_Facet_Crossing_Event.cc:41-47)
+            const int to_col = __popc(__ballot_sync(kFullMask, next == kStCollision));
+            const int to_cen = __popc(__ballot_sync(kFullMask, next == kStCensus));
+            const int to_load = __popc(__ballot_sync(kFullMask, next == kStLoad));
+            const int to_snd = (kPeer || a.im.n_ranks > 1) ? __popc(__ballot_sync(kFullMask, next == kStSend)) : 0;
+#if QSB_VALIDATION
+            const unsigned n_slow = __reduce_add_sync(kFullMask, slow), n_mis = __reduce_add_sync(kFullMask, mismatch);
+#endif
+            if (lane == 0)
+            {
+                w.n[kNSeg] -= to_col + to_cen + to_load + to_snd;        // the rest of the batch stays in SEGMENT
+                w.n[kNCol] += to_col; w.n[kNCen] += to_cen; w.n[kNLoad] += to_load; w.n[kNSnd] += to_snd;
+                w.retired += (unsigned)to_load;
+                w.tally[kTalSegments] += min(total, 32u); w.tally[kTalCensus] += (unsigned)to_cen; w.tally[kTalEscapes] += (unsigned)to_load;
+#if QSB_VALIDATION
+                w.tally[kTalSlow] += n_slow; w.tally[kTalMismatch] += n_mis;
+#endif
+            }
+            continue;
+        }
+
+        if (type == kStCollision)
+        {
+            const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStCollision || st == kStTail; });
+            const bool active = lane < total;
+            const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
+            Counters c = {};
+            Particle p;
+            bool tail = false;
+            double energy0 = 0.0, angle0 = 0.0, energy1 = 0.0, angle1 = 0.0, energy2 = 0.0, angle2 = 0.0, energy3 = 0.0, angle3 = 0.0;
+            int n_out = 0;
+            if (active)
+            {
+                tail = s.state[slot] == kStTail;
+                p.x = s.x[slot]; p.y = s.y[slot]; p.z = s.z[slot];
+                p.alpha = s.alpha[slot]; p.beta = s.beta[slot]; p.gamma = s.gamma[slot];
+                p.energy = s.energy[slot]; p.weight = s.weight[slot]; p.ttc = s.ttc[slot]; p.age = s.age[slot];
+                p.nmfp = s.nmfp[slot]; p.nseg = s.nseg[slot]; p.speed = s.speed[slot];
+#if QSB_VALIDATION
+                p.vx = s.vx[slot]; p.vy = s.vy[slot]; p.vz = s.vz[slot];
+#endif
+                p.seed = s.seed[slot];
+                load_head(s, slot, p);
+                p.cell = s.cell[slot];
+                p.num_collisions = s.num_collisions[slot]; p.breed = s.breed[slot]; p.species = s.species[slot];
+                p.group = s.group[slot];
+                p.last_event = QSB_EV_COLLISION; p.facet = 0;
+                // the total cross section the segment ended on (MC_Segment_Outcome leaves it in the particle, src/MC_Segment_Outcome.cc:60-66)
+                p.total_xs = __ldg(a.im.xs_pair + (size_t)cell_material(p.head) * a.im.n_groups + p.group).x;
+                energy0 = p.energy; angle0 = p.nmfp;                    // a raw child carries its sampled outcome in these two fields
+                n_out = 1;
+                if (!tail) n_out = collision_head(a, p, c, energy0, angle0, energy1, angle1, energy2, angle2, energy3, angle3);
+            }
+            // balance tallies of the batch (src/CollisionEvent.cc:104-119), from ballots: nothing per-thread stays live
+            const unsigned t_col = __popc(__ballot_sync(kFullMask, c.collisions != 0u));
+            const unsigned t_abs = __popc(__ballot_sync(kFullMask, c.absorbs != 0u));
+            const unsigned fis_mask = __ballot_sync(kFullMask, c.fissions != 0u);
+            const unsigned t_pro = fis_mask ? __reduce_add_sync(kFullMask, c.produced) : 0u;
+#if QSB_VALIDATION
+            const unsigned t_sca = __popc(__ballot_sync(kFullMask, c.scatters != 0u));
+            const unsigned t_look = __reduce_add_sync(kFullMask, c.lookups), t_mis = __reduce_add_sync(kFullMask, c.mismatch);
+#endif
+            // secondaries of the whole batch: vault slots and the in-flight count with one atomic each
+            const unsigned n_child = (active && !tail && n_out > 1) ? (unsigned)(n_out - 1) : 0u;
+            unsigned incl = n_child;
+            if (fis_mask)
+            {
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1)
+                {
+                    const unsigned up = __shfl_up_sync(kFullMask, incl, d);
+                    if ((int)lane >= d) incl += up;
+                }
+            }
+            const unsigned n_children = fis_mask ? __shfl_sync(kFullMask, incl, 31) : 0u;
+            if (n_children)
+            {
+                unsigned long long cb = 0;
+                if (lane == 0)
+                {
+                    cb = atomicAdd(a.tail, (unsigned long long)n_children);
+                    atomicAdd(a.inflight, (unsigned long long)n_children);
+                }
+                cb = __shfl_sync(kFullMask, cb, 0) - a.n_in;
+                if (n_child)
+                {
+                    const unsigned long long first = cb + (incl - n_child);
+                    if (first + n_child > a.proc.capacity)
+                    {
+                        atomicOr(&a.ctl->overflow, 1u);
+                        atomicAdd(a.inflight, 0ull - (unsigned long long)n_child);
+                    }
+                    else
+                    {
+                        write_raw_child(a, first, p, qs_rng_spawn(&p.seed), energy1, angle1);
+                        if (n_child > 1u) write_raw_child(a, first + 1, p, qs_rng_spawn(&p.seed), energy2, angle2);
+                        if (n_child > 2u) write_raw_child(a, first + 2, p, qs_rng_spawn(&p.seed), energy3, angle3);
+                        s.pub_first[threadIdx.x] = first; s.pub_n[threadIdx.x] = n_child;       // published at the top of the next iteration
+                    }
+                }
+            }
+            bool absorbed = false;
+            if (active)
+            {
+                if (n_out > 0)
+                {
+                    collision_tail(a, p, energy0, angle0, tail || n_out > 1);
+                    s.energy[slot] = p.energy;
+                    s.alpha[slot] = p.alpha; s.beta[slot] = p.beta; s.gamma[slot] = p.gamma;
+                    s.speed[slot] = p.speed; s.nmfp[slot] = p.nmfp; s.ttc[slot] = p.ttc; s.age[slot] = p.age;
+#if QSB_VALIDATION
+                    s.vx[slot] = p.vx; s.vy[slot] = p.vy; s.vz[slot] = p.vz;
+#endif
+                    s.seed[slot] = p.seed;
+                    s.group[slot] = (unsigned short)p.group;
+                    s.last_event[slot] = (unsigned char)QSB_EV_COLLISION;
+                    s.state[slot] = (unsigned char)kStSegment;
+                }
+                else { absorbed = true; s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad; }
+            }
+            const int n_act = (int)min(total, 32u);
+            const int n_gone = __popc(__ballot_sync(kFullMask, absorbed));
+            if (lane == 0)
+            {
+                w.n[kNCol] -= n_act; w.n[kNSeg] += n_act - n_gone; w.n[kNLoad] += n_gone;
+                w.retired += (unsigned)n_gone;
+                if (n_children) w.has_pub = 1u;
+                w.tally[kTalCollisions] += t_col; w.tally[kTalAbsorbs] += t_abs;
+                if (fis_mask) { w.tally[kTalFissions] += (unsigned)__popc(fis_mask); w.tally[kTalProduced] += t_pro; }
+#if QSB_VALIDATION
+                w.tally[kTalScatters] += t_sca; w.tally[kTalLookups] += t_look; w.tally[kTalMismatch] += t_mis;
+#endif
+            }
+            continue;
+        }
+
+        if (type == kStCensus)
+        {
+            const int n_act = wq_census(a, s, warp, lane);
+            if (lane == 0) { w.n[kNCen] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
+            continue;
+        }
+
+        {
+            const int n_act = wq_send<kPeer>(a, s, warp, lane);
+            if (lane == 0) { w.n[kNSnd] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
+        }
+    }
+
+    // flush the warp's balance counters: one atomic per counter
+    __syncwarp();
+    if (lane == 0)
+    {
+        const unsigned* t = s.w[warp].tally;
+        unsigned long long* b = a.ctl->balance;
+#if QSB_VALIDATION
+        const unsigned s_sca = t[kTalScatters];
+#else
+        // every collision of the fast build is one of the three reaction types (an undefined type would have been rejected by the host model)
+        const unsigned s_sca = t[kTalCollisions] - t[kTalAbsorbs] - t[kTalFissions];
+#endif
+        if (t[kTalSegments]) atomicAdd(b + QSB_BAL_NUM_SEGMENTS, (unsigned long long)t[kTalSegments]);
+        if (t[kTalCollisions]) atomicAdd(b + QSB_BAL_COLLISION, (unsigned long long)t[kTalCollisions]);
+        if (s_sca) atomicAdd(b + QSB_BAL_SCATTER, (unsigned long long)s_sca);
+        if (t[kTalAbsorbs]) atomicAdd(b + QSB_BAL_ABSORB, (unsigned long long)t[kTalAbsorbs]);
+        if (t[kTalFissions]) atomicAdd(b + QSB_BAL_FISSION, (unsigned long long)t[kTalFissions]);
+        if (t[kTalProduced]) atomicAdd(b + QSB_BAL_PRODUCE, (unsigned long long)t[kTalProduced]);
+        if (t[kTalEscapes]) atomicAdd(b + QSB_BAL_ESCAPE, (unsigned long long)t[kTalEscapes]);
+        if (t[kTalCensus]) atomicAdd(b + QSB_BAL_CENSUS, (unsigned long long)t[kTalCensus]);
+        if (t[kTalLookups]) atomicAdd(&a.ctl->n_lookups, (unsigned long long)t[kTalLookups]);
+        if (t[kTalSlow]) atomicAdd(&a.ctl->slow_geometry, (unsigned long long)t[kTalSlow]);
+        if (t[kTalMismatch]) atomicAdd(&a.ctl->geometry_mismatch, (unsigned long long)t[kTalMismatch]);
+    }
+}
+
+} // namespace
+
+#if QSB_VALIDATION
+#define QSB_EVT_LAUNCH_NAME launch_track_event_validation
+#define QSB_EVT_ATTR_NAME track_event_kernel_attributes_validation
+#else
+#define QSB_EVT_LAUNCH_NAME launch_track_event_fast
+#define QSB_EVT_ATTR_NAME track_event_kernel_attributes_fast
+#endif
+
+void QSB_EVT_LAUNCH_NAME(const TrackArgs& a, int grid, cudaStream_t s)
+{
+    if (a.peer_mode) track_warpq_kernel<QSB_VALIDATION, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    else             track_warpq_kernel<QSB_VALIDATION, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+}
+
+// registers per thread, resident blocks per SM, threads per block, shared-memory bytes per block, particle slots per block
+void QSB_EVT_ATTR_NAME(int* regs, int* max_blocks_per_sm, int* threads, int* smem_bytes, int* slots)
+{
+    cudaFuncSetAttribute(track_warpq_kernel<QSB_VALIDATION, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqShared));
+    cudaFuncSetAttribute(track_warpq_kernel<QSB_VALIDATION, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqShared));
+    cudaFuncAttributes attr;
+    int r = 0;
+    if (cudaFuncGetAttributes(&attr, track_warpq_kernel<QSB_VALIDATION, 0>) == cudaSuccess) r = attr.numRegs;
+    if (cudaFuncGetAttributes(&attr, track_warpq_kernel<QSB_VALIDATION, 1>) == cudaSuccess && attr.numRegs > r) r = attr.numRegs;
+    if (regs) *regs = r;
+    int n0 = 0, n1 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, track_warpq_kernel<QSB_VALIDATION, 0>, kWqThreads, sizeof(WqShared));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, track_warpq_kernel<QSB_VALIDATION, 1>, kWqThreads, sizeof(WqShared));
+    if (max_blocks_per_sm) *max_blocks_per_sm = n0 < n1 ? n0 : n1;
+    if (threads) *threads = kWqThreads;
+    if (smem_bytes) *smem_bytes = (int)sizeof(WqShared);
+    if (slots) *slots = kWqSlots;
+}
+
+} // namespace qsb

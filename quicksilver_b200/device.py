@@ -11,10 +11,12 @@ from ._capi import BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYPE, QsbError
 
 class DeviceContext:
     def __init__(self, image, dt, device=0, validation=True, particle_capacity=0, send_capacity=0,
-                 threads_per_block=0, blocks_per_sm=0, check_geometry=False, check_reactions=False):
+                 threads_per_block=0, blocks_per_sm=0, check_geometry=False, check_reactions=False, event=None):
+        """event: False = history-based tracking kernel (tracking_mode bit 0 set), True / None = the library default, the
+        event-based kernel (QSB_TRACKING=history|event in the environment overrides either)"""
         self._lib = _capi.lib()
         self.image = image
-        self.opt = _capi.Options(int(bool(validation)), (2 if check_geometry else 0) | (4 if check_reactions else 0), int(particle_capacity), int(send_capacity),
+        self.opt = _capi.Options(int(bool(validation)), (1 if event is False else 0) | (2 if check_geometry else 0) | (4 if check_reactions else 0), int(particle_capacity), int(send_capacity),
                                  int(threads_per_block), int(blocks_per_sm))
         self._h = C.c_void_p()
         rc = self._lib.qsb_create(int(device), C.byref(image), float(dt), C.byref(self.opt), C.byref(self._h))

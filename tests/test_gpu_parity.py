@@ -28,13 +28,16 @@ CASES = {
 }
 
 
-def _run_case(tmp_path, name, validation=True, check_geometry=False, check_reactions=False):
+KERNELS = ["event", "history"]      # the two tracking kernels (tracking_mode bit 0): same results bit for bit
+
+
+def _run_case(tmp_path, name, validation=True, check_geometry=False, check_reactions=False, kernel="event"):
     deck_name, over, cycles = CASES[name]
     deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
     mc = host.MonteCarlo(["-i", deck])
     dt = mc.get_double("dt")
     ctx = device.DeviceContext(mc.image, dt, validation=validation, particle_capacity=1 << 20, check_geometry=check_geometry,
-                               check_reactions=check_reactions)
+                               check_reactions=check_reactions, event=(kernel == "event"))
     out = []
     for _ in range(cycles):
         mc.cycle_init()
@@ -54,9 +57,10 @@ def _run_case(tmp_path, name, validation=True, check_geometry=False, check_react
     return out
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_validation_build_matches_oracle_bit_for_bit(tmp_path, name):
-    for cycle, (census, balance, flux, flux_sum, want, stats) in enumerate(_run_case(tmp_path, name)):
+def test_validation_build_matches_oracle_bit_for_bit(tmp_path, name, kernel):
+    for cycle, (census, balance, flux, flux_sum, want, stats) in enumerate(_run_case(tmp_path, name, kernel=kernel)):
         assert np.array_equal(balance, want.balance), "cycle %d balance %s != %s" % (cycle, balance, want.balance)
         got, ref = H.sort_particles(census), H.sort_particles(want.census)
         assert len(got) == len(ref)
@@ -68,33 +72,36 @@ def test_validation_build_matches_oracle_bit_for_bit(tmp_path, name):
         assert stats.n_processed >= len(census)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", ["cts2_small", "p2_small", "allescape_4dom", "nofission_octant"])
-def test_filtered_geometry_agrees_with_full_search(tmp_path, name):
+def test_filtered_geometry_agrees_with_full_search(tmp_path, name, kernel):
     """check mode: every segment evaluates both the filtered single-facet path and the reference's full
     24-facet search; they must agree on facet, distance and coordinate bit for bit, and the filtered path
     must carry nearly all segments."""
-    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_geometry=True):
+    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_geometry=True, kernel=kernel):
         assert stats.diag["compact_geometry"] == 1
         assert stats.diag["geometry_mismatch"] == 0
         assert stats.diag["slow_geometry"] <= 0.01 * float(balance[BAL["num_segments"]]) + 10
         assert np.array_equal(balance, want.balance)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", ["cts2_small", "p1_small", "p2_small", "nonflat_supercritical", "allabsorb_4dom"])
-def test_direct_reaction_selection_agrees_with_subtraction_chain(tmp_path, name):
+def test_direct_reaction_selection_agrees_with_subtraction_chain(tmp_path, name, kernel):
     """check mode: every collision evaluates both the one-division filtered selection and the reference's
     subtraction chain (src/CollisionEvent.cc:59-83); they must pick the same (isotope, reaction) every time."""
-    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_reactions=True):
+    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, check_reactions=True, kernel=kernel):
         assert stats.diag["geometry_mismatch"] == 0          # the counter is shared by both check modes
         assert np.array_equal(balance, want.balance)
         assert int(balance[BAL["collision"]]) > 0
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name", ["cts2_small", "p1_small"])
-def test_fast_build_within_statistical_tolerance(tmp_path, name):
+def test_fast_build_within_statistical_tolerance(tmp_path, name, kernel):
     """fast build (FMA contraction + CUDA libm): histories may differ in the last bits, tallies must agree
     statistically -- in practice they are identical or off by a handful of events."""
-    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, validation=False):
+    for census, balance, flux, flux_sum, want, stats in _run_case(tmp_path, name, validation=False, kernel=kernel):
         for key in ("num_segments", "collision", "scatter", "absorb", "fission", "census"):
             a, b = float(balance[BAL[key]]), float(want.balance[BAL[key]])
             assert abs(a - b) <= 0.01 * max(b, 100.0), (key, a, b)
@@ -132,15 +139,16 @@ def test_capacity_overflow_is_reported(tmp_path):
     ctx.close()
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("name,census_capacity", [("cts2_small", None), ("nonflat_supercritical", 1000), ("allescape_4dom", None)])
-def test_streamed_host_buffers_match_oracle(tmp_path, name, census_capacity):
+def test_streamed_host_buffers_match_oracle(tmp_path, name, census_capacity, kernel):
     """qsb_track_host: host vault streamed in (pageable numpy memory -> bounce-buffer staging), census streamed
     back in record form; with a small census buffer the excess is fetched with qsb_get_census_range."""
     deck_name, over, _ = CASES[name]
     deck = decks.write_deck(decks.derive(deck_name, over), str(tmp_path / (name + ".inp")))
     mc = host.MonteCarlo(["-i", deck])
     dt = mc.get_double("dt")
-    ctx = device.DeviceContext(mc.image, dt, validation=True, particle_capacity=1 << 20)
+    ctx = device.DeviceContext(mc.image, dt, validation=True, particle_capacity=1 << 20, event=(kernel == "event"))
     mc.cycle_init()
     vault = mc.processing()
     ctx.cycle_begin()
