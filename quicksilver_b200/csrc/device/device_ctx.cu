@@ -579,6 +579,12 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         if (const char* e = std::getenv("QSB_BLOCKS_PER_SM"))         // occupancy experiments only
             if (std::atoi(e) > 0) c->blocks_per_sm = std::min(c->blocks_per_sm, std::atoi(e));
         c->grid = c->sm_count * c->blocks_per_sm;
+        if (std::getenv("QSB_TRACE"))
+            std::fprintf(stderr, "[qsb] rank %d: %s kernel (%s build), %d registers, %d threads x %d blocks per SM, grid %d, shared memory %d B per block; "
+                         "compact geometry %d, brick neighbours %d (strides %d %d %d), compact reaction table %d\n",
+                         c->my_rank, c->event_mode ? "event-based" : "history-based", c->opt.validation ? "validation" : "fast", c->regs, c->block,
+                         c->blocks_per_sm, c->grid, c->evt_smem, im.compact, im.brick, im.brick_stride[0], im.brick_stride[1], im.brick_stride[2],
+                         im.xs_compact ? im.compact_react : 0);
         QSB_CUDA(cudaStreamSynchronize(c->stream));
     }
     catch (const CudaFailure& f)

@@ -24,6 +24,8 @@
 // are appended to the vault and picked up by whichever warp redeems their ticket), the global in-flight counter, the
 // census append, the peer deposits and the termination protocol.  Results are independent of the scheduling: a
 // history's random numbers come from its own stream and tallies are sums (tests: bit-identical census and balance).
+#include <cstdlib>
+
 #include "track_physics.cuh"
 
 namespace qsb {
@@ -121,6 +123,10 @@ constexpr int kWqK = (kWq + 31) / 32;               // ... per lane of bookkeepi
 constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
+#ifndef QSB_WQ_SERVICE
+#define QSB_WQ_SERVICE 24
+#endif
+constexpr int kService = QSB_WQ_SERVICE;            // parked slots (census / send / empty) a warp lets gather before it services them
 static_assert(kWq % 4 == 0 && kWq >= 32 && kWq <= 256, "a warp's slots: at least a batch, slot numbers fit a byte");
 
 enum { kStLoad = 0, kStSegment, kStCollision, kStTail, kStCensus, kStSend };
@@ -270,6 +276,7 @@ __device__ __noinline__ int wq_census(const TrackArgs& a, WqShared& s, unsigned 
 template <int kPeer>
 __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
 {
+    const long long t_enter = clock64();
     const unsigned base = warp * kWq;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStSend; });
     const bool active = lane < total;
@@ -323,6 +330,11 @@ __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned wa
         }
     }
     if (active) { s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad; }
+    if (kPeer && a.peer_mode && lane == 0)
+    {
+        atomicAdd(&peer_control(a, a.my_rank)->send_cycles, (unsigned long long)(clock64() - t_enter));
+        atomicAdd(&peer_control(a, a.my_rank)->send_calls, 1ull);
+    }
     return (int)min(total, 32u);
 }
 
@@ -390,19 +402,21 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         }
 
         // ---- which event next ----
+        // Slots whose history has ended (census record to store, particle to ship to a peer) or that are empty do not take
+        // part in the tracking batches: they are "parked" until serviced.  Servicing comes FIRST once kService of them have
+        // gathered, so that the warp keeps most of its slots in flight; then full collision batches (the longest event), then
+        // full segment batches, then whatever is largest.
         const bool may_take = n_wait < 32;              // tickets are handed out in order: holding unredeemable ones means the queue's tail is reached
         const int n_fill = may_take ? n_load - n_wait : 0;
         int type;
-        if (n_col >= 32) type = kStCollision;
+        if (n_cen + n_snd + n_fill >= kService) type = (n_snd >= n_cen && n_snd >= n_fill) ? kStSend : (n_cen >= n_fill ? kStCensus : kStLoad);
+        else if (n_col >= 32) type = kStCollision;
         else if (n_seg >= 32) type = kStSegment;
-        else if (n_fill >= 16) type = kStLoad;
-        else if (n_cen >= 32) type = kStCensus;
-        else if (n_snd >= 32) type = kStSend;
-        else if (n_fill > 0) type = kStLoad;
         else
         {
             type = kStSegment; int best = n_seg;
             if (n_col > best) { best = n_col; type = kStCollision; }
+            if (n_fill > best) { best = n_fill; type = kStLoad; }
             if (n_cen > best) { best = n_cen; type = kStCensus; }
             if (n_snd > best) { best = n_snd; type = kStSend; }
             if (best == 0)
@@ -695,7 +709,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
 
 void QSB_EVT_LAUNCH_NAME(const TrackArgs& a, int grid, cudaStream_t s)
 {
-    if (a.peer_mode) track_warpq_kernel<QSB_VALIDATION, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    // QSB_FORCE_PEER_INSTANCE=1 (measurements only): run the instance that carries the peer-exchange code on a single GPU
+    static const bool force_peer_instance = std::getenv("QSB_FORCE_PEER_INSTANCE") != nullptr;
+    if (a.peer_mode || force_peer_instance) track_warpq_kernel<QSB_VALIDATION, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
     else             track_warpq_kernel<QSB_VALIDATION, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
 }
 

@@ -51,10 +51,10 @@ def test_unknown_keys_are_ignored_and_bad_decks_are_reported(tmp_path):
 
 
 def test_kernel_facet_tables_follow_from_the_reference_tables():
-    """c_facet_points / c_facet_of_edge in track_kernels.cu: the first is the reference's nodeIndirect table
+    """c_facet_points / c_facet_of_edge in track_physics.cuh: the first is the reference's nodeIndirect table
     (src/MC_Domain.cc:41-50); the second (face, edge) -> facet map is derived here from it and the 14-point
     layout of a cell (8 corners in 000,100,010,110,001,... order, then the +x,-x,+y,-y,+z,-z face centres)."""
-    src = open(os.path.join(H.ROOT, "quicksilver_b200", "csrc", "device", "track_kernels.cu")).read()
+    src = open(os.path.join(H.ROOT, "quicksilver_b200", "csrc", "device", "track_physics.cuh")).read()
     m = re.search(r"c_facet_points\[24\]\[4\]\s*=\s*\{(.*?)\};", src, re.S)
     pts = np.array([int(v) for v in re.findall(r"-?\d+", m.group(1))]).reshape(24, 4)[:, :3]
     assert np.array_equal(pts, np.array(FACET_POINTS))
