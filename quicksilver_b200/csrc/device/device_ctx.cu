@@ -1009,6 +1009,13 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         uint32_t n_launch = 0;
         // tickets handed out past the tail by the previous call were never redeemed: restart at the consumed mark
         c->h_ctl->head = c->consumed;
+        if (c->event_mode)
+        {
+            // two queues: streamed input records [0, n_in) and vault slots (tickets >= n_in), see wq_load
+            c->h_ctl->head_in = std::min<unsigned long long>(c->consumed, c->n_in_aos);
+            c->h_ctl->head = std::max<unsigned long long>(c->consumed, c->n_in_aos);
+            QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->head_in, &c->h_ctl->head_in, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+        }
         c->h_ctl->inflight = c->pending_inflight;
         c->pending_inflight = 0;
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->head, &c->h_ctl->head, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));

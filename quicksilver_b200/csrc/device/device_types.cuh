@@ -108,6 +108,8 @@ struct DevControl
     unsigned long long pad3[31];
     unsigned long long in_ready;        // host-buffer streaming: input records [0, in_ready) have landed in HBM
     unsigned long long pad4[31];
+    unsigned long long head_in;         // event kernel, host-buffer streaming: next unclaimed ticket of the INPUT queue [0, n_in); `head` then
+    unsigned long long pad5[31];        // serves the vault slots only (tickets >= n_in), so secondaries do not queue behind the whole input
     unsigned long long slow_geometry;   // segments that took the full 24-facet path
     unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];

@@ -124,7 +124,7 @@ constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
 #ifndef QSB_WQ_SERVICE
-#define QSB_WQ_SERVICE 24
+#define QSB_WQ_SERVICE 48
 #endif
 constexpr int kService = QSB_WQ_SERVICE;            // parked slots (census / send / empty) a warp lets gather before it services them
 static_assert(kWq % 4 == 0 && kWq >= 32 && kWq <= 256, "a warp's slots: at least a batch, slot numbers fit a byte");
@@ -135,14 +135,14 @@ enum { kStLoad = 0, kStSegment, kStCollision, kStTail, kStCensus, kStSend };
 // budget goes, and anything that stays live across it is spilled to local memory (measured: the spilled per-thread balance
 // counters and slot counts alone were 15 % of all stall samples).  Everybody reads it at the top of an iteration (one
 // broadcast load each), lane 0 updates it at the end of a batch.
-enum { kNSeg = 0, kNCol, kNCen, kNSnd, kNLoad, kNWait, kNCounts };
+enum { kNSeg = 0, kNCol, kNCen, kNSnd, kNLoad, kNWait, kNWaitVault, kNCounts };
 struct WqWarpState
 {
-    int n[kNCounts];                // slots per state; kNWait: tickets held that could not be redeemed at the last LOAD
+    int n[kNCounts];                // slots per state; kNWait / kNWaitVault: input / vault tickets held that could not be redeemed at the last LOAD
     unsigned retired;               // histories ended, not yet subtracted from the global in-flight count
     unsigned backoff;
     unsigned has_pub;               // some lane wrote fission secondaries in the last collision batch (pub_first / pub_n): publish them
-    unsigned pad;
+    unsigned input_left;            // streamed input records may still be unclaimed (cleared once the input queue is seen empty)
     unsigned tally[12];             // the warp's balance counters (kTal*), flushed once at kernel end
     unsigned long long in_seen;     // host-buffer streaming: last value of ctl->in_ready the warp has seen
     unsigned long long t_start;
@@ -181,27 +181,70 @@ __device__ __forceinline__ unsigned wq_gather(WqShared& s, unsigned warp, unsign
 
 // LOAD: every slot of the warp without a particle; empty ones take a ticket (one global atomic per batch of 32), tickets
 // are redeemed once the vault slot they name has been written -- the history kernel's protocol (its service phase).
-struct WqLoaded { int to_segment, to_tail, waiting; };
-__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take)
+//
+// Two queues.  Tickets [0, n_in) are the records of a streamed host vault (host-buffer call: they land in HBM chunk by chunk
+// while the kernel runs, PCIe-paced), tickets >= n_in are vault slots (initial population of a resident cycle, fission
+// secondaries, arrivals from peers).  With ONE queue every secondary waits behind the whole input: once the kernel has caught
+// up with the DMA front all slots hold input tickets, the secondaries pile up and are tracked -- and their census records
+// sent back -- only after the last input chunk has landed (Coral2_P1: ~10 ms of a 38 ms call).  So the input has its own
+// head (ctl->head_in), and while input is left a warp takes VAULT tickets only for slots that exist (below the tail) and
+// input tickets for the rest of its empty slots; an input ticket is always redeemed eventually (the DMA front moves on its
+// own), a vault ticket past the final tail never is -- harmless, the cycle ends on the in-flight count -- and the few of
+// them a race can leave a warp with (two warps reading the same tail) are bounded by `may_take_vault`.
+struct WqLoaded { int to_segment, to_tail, waiting_in, waiting_vault; };
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault)
 {
     const unsigned base = warp * kWq;
     unsigned long long in_seen = s.w[warp].in_seen;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStLoad; });
-    WqLoaded out = { 0, 0, 0 };
+    WqLoaded out = { 0, 0, 0, 0 };
     for (unsigned first = 0; first < total; first += 32u)
     {
         const bool active = first + lane < total;
         const unsigned slot = base + (active ? s.list[warp][first + lane] : 0u);
         unsigned long long ticket = active ? s.id[slot] : kNoTicket;
-        const bool want = active && ticket == kNoTicket && may_take;
+        const bool want = active && ticket == kNoTicket;
         const unsigned want_mask = __ballot_sync(kFullMask, want);
         if (want_mask)
         {
-            unsigned long long tb = 0;
+            const unsigned n_want = __popc(want_mask);
+            unsigned long long tb_v = 0, tb_in = 0;
+            unsigned k_v = 0, k_in = 0;
             const unsigned leader = __ffs(want_mask) - 1;
-            if (lane == leader) tb = atomicAdd(&a.ctl->head, (unsigned long long)__popc(want_mask));
-            tb = __shfl_sync(kFullMask, tb, leader);
-            if (want) ticket = tb + __popc(want_mask & ((1u << lane) - 1u));
+            if (lane == leader)
+            {
+                const bool input_left = a.n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < a.n_in;
+                if (input_left)
+                {
+                    if (may_take_vault)
+                    {
+                        const unsigned long long t = ld_relaxed_u64(a.tail), h = ld_relaxed_u64(&a.ctl->head);
+                        k_v = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
+                    }
+                    if (may_take_in) k_in = n_want - k_v;
+                }
+                else
+                {
+                    s.w[warp].input_left = 0u;
+                    k_v = may_take_vault ? n_want : 0u;
+                }
+                if (k_v) tb_v = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
+                if (k_in) tb_in = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
+            }
+            tb_v = __shfl_sync(kFullMask, tb_v, leader); tb_in = __shfl_sync(kFullMask, tb_in, leader);
+            k_v = __shfl_sync(kFullMask, k_v, leader); k_in = __shfl_sync(kFullMask, k_in, leader);
+            if (want)
+            {
+                const unsigned r = __popc(want_mask & ((1u << lane) - 1u));
+                if (r < k_v) ticket = tb_v + r;
+                else if (r - k_v < k_in && tb_in + (r - k_v) < a.n_in) ticket = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
+            }
         }
         bool ready = false;
         if (active && ticket != kNoTicket)
@@ -237,7 +280,8 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         else if (active) s.id[slot] = ticket;
         out.to_segment += __popc(__ballot_sync(kFullMask, state == kStateSegment));
         out.to_tail += __popc(__ballot_sync(kFullMask, state == kStateTail));
-        out.waiting += __popc(__ballot_sync(kFullMask, active && !ready && ticket != kNoTicket));
+        out.waiting_in += __popc(__ballot_sync(kFullMask, active && !ready && ticket < a.n_in));
+        out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket != kNoTicket && ticket >= a.n_in));
     }
     // keep the highest DMA front any lane has seen
 #pragma unroll
@@ -381,7 +425,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         WqWarpState& w0 = s.w[warp];
         for (int k = 0; k < kNCounts; ++k) w0.n[k] = 0;
         w0.n[kNLoad] = kWq;
-        w0.retired = 0u; w0.backoff = 64u; w0.has_pub = 0u; w0.pad = 0u;
+        w0.retired = 0u; w0.backoff = 64u; w0.has_pub = 0u; w0.input_left = 1u;
         for (int k = 0; k < 12; ++k) w0.tally[k] = 0u;
         w0.in_seen = 0ull; w0.t_start = global_timer_ns();
     }
@@ -390,7 +434,8 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
     {
         __syncwarp();
         WqWarpState& w = s.w[warp];
-        const int n_seg = w.n[kNSeg], n_col = w.n[kNCol], n_cen = w.n[kNCen], n_snd = w.n[kNSnd], n_load = w.n[kNLoad], n_wait = w.n[kNWait];
+        const int n_seg = w.n[kNSeg], n_col = w.n[kNCol], n_cen = w.n[kNCen], n_snd = w.n[kNSnd], n_load = w.n[kNLoad];
+        const int n_wait_in = w.n[kNWait], n_wait_vault = w.n[kNWaitVault], n_wait = n_wait_in + n_wait_vault;
         const unsigned has_pub = w.has_pub;
         __syncwarp();                                   // everybody has read the state before lane 0 may change it
         if (has_pub)
@@ -406,8 +451,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         // part in the tracking batches: they are "parked" until serviced.  Servicing comes FIRST once kService of them have
         // gathered, so that the warp keeps most of its slots in flight; then full collision batches (the longest event), then
         // full segment batches, then whatever is largest.
-        const bool may_take = n_wait < 32;              // tickets are handed out in order: holding unredeemable ones means the queue's tail is reached
-        const int n_fill = may_take ? n_load - n_wait : 0;
+        // tickets of a queue are handed out in order: holding unredeemable ones means its end (DMA front / tail) is reached
+        const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < (a.n_in ? 16 : 32);
+        const int n_fill = (may_take_in || may_take_vault) ? n_load - n_wait : 0;
         int type;
         if (n_cen + n_snd + n_fill >= kService) type = (n_snd >= n_cen && n_snd >= n_fill) ? kStSend : (n_cen >= n_fill ? kStCensus : kStLoad);
         else if (n_col >= 32) type = kStCollision;
@@ -451,11 +497,11 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         if (type == kStLoad)
         {
             if (lane == 0 && w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
-            const WqLoaded got = wq_load(a, s, warp, lane, may_take);
+            const WqLoaded got = wq_load(a, s, warp, lane, may_take_in, may_take_vault);
             if (lane == 0)
             {
                 w.n[kNSeg] += got.to_segment; w.n[kNCol] += got.to_tail; w.n[kNLoad] -= got.to_segment + got.to_tail;
-                w.n[kNWait] = got.waiting;
+                w.n[kNWait] = got.waiting_in; w.n[kNWaitVault] = got.waiting_vault;
                 if (got.to_segment | got.to_tail) w.backoff = 64u;
             }
             continue;
