@@ -321,8 +321,12 @@ uint64_t qsb_exchange_record_bytes(void);
  * it is still tracking, and global termination (the reference's allreduce of sends/receives,
  * src/MC_Particle_Buffer.cc:601-618) is decided on the devices.  A cycle is then ONE qsb_track call per rank, no rounds.
  * Contract: all ranks use the same particle_capacity (qsb_peer_export returns it for the caller to compare) and call
- * qsb_track the same number of times.  watchdog_seconds (0 = 60): a launch that has not terminated by then is abandoned
- * on every rank and qsb_track fails. */
+ * qsb_track the same number of times, with a cross-rank synchronisation point between two peer-mode launches: a rank must
+ * not start launch k+1 before every rank has returned from launch k (the termination waves compare every rank's launch
+ * epoch; a rank that ran ahead would keep a slower one waiting for its watchdog).  The reference's cycle has such a point
+ * for free -- cycleFinalize's allreduce of the balance tallies, src/Tallies.cc:75-93 via src/main.cc:310-324 -- and so do
+ * quicksilver_b200.driver and the qs_b200 executable; a caller that launches back to back must add its own barrier.
+ * watchdog_seconds (0 = 60): a launch that has not terminated by then is abandoned on every rank and qsb_track fails. */
 #define QSB_MAX_PEERS 8
 #define QSB_PEER_HANDLE_BYTES 64
 int  qsb_peer_export(qsb_ctx* ctx, void* handle /* [QSB_PEER_HANDLE_BYTES] */, uint64_t* vault_capacity);

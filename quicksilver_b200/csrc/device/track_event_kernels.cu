@@ -124,9 +124,10 @@ constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
 #ifndef QSB_WQ_SERVICE
-#define QSB_WQ_SERVICE 48
+#define QSB_WQ_SERVICE (QSB_WQ_SLOTS_PER_WARP / 2)
 #endif
-constexpr int kService = QSB_WQ_SERVICE;            // parked slots (census / send / empty) a warp lets gather before it services them
+constexpr int kService = QSB_WQ_SERVICE;            // parked slots (census / send / empty) a warp lets gather before it services them:
+                                                    // half of its slots (measured, Coral2_P1: 24 -> 15.6 ms, 32 -> 15.0, 48 -> 14.4)
 static_assert(kWq % 4 == 0 && kWq >= 32 && kWq <= 256, "a warp's slots: at least a batch, slot numbers fit a byte");
 
 enum { kStLoad = 0, kStSegment, kStCollision, kStTail, kStCensus, kStSend };
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         WqWarpState& w = s.w[warp];
         const int n_seg = w.n[kNSeg], n_col = w.n[kNCol], n_cen = w.n[kNCen], n_snd = w.n[kNSnd], n_load = w.n[kNLoad];
         const int n_wait_in = w.n[kNWait], n_wait_vault = w.n[kNWaitVault], n_wait = n_wait_in + n_wait_vault;
-        const unsigned has_pub = w.has_pub;
+        const unsigned has_pub = w.has_pub, w_input_left = w.input_left;
         __syncwarp();                                   // everybody has read the state before lane 0 may change it
         if (has_pub)
         {
@@ -448,23 +449,27 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
 
         // ---- which event next ----
         // Slots whose history has ended (census record to store, particle to ship to a peer) or that are empty do not take
-        // part in the tracking batches: they are "parked" until serviced.  Servicing comes FIRST once kService of them have
-        // gathered, so that the warp keeps most of its slots in flight; then full collision batches (the longest event), then
-        // full segment batches, then whatever is largest.
+        // part in the tracking batches: they are "parked".  Once kService of them have gathered -- or when no full tracking
+        // batch is left and they outnumber what is -- the warp runs its SERVICE phase: every pending send, every pending
+        // census record, then a refill of all empty slots, in one go (a particle bound for a peer must not sit in its slot
+        // until 31 others have joined it: at ~140 sends per warp and cycle that parks a sixth of the warp's slots for good;
+        // measured on 2 GPUs).  Otherwise: full collision batches (the longest event) before full segment batches.
         // tickets of a queue are handed out in order: holding unredeemable ones means its end (DMA front / tail) is reached
+        // (n_fill: empty slots a LOAD can be expected to give a ticket to -- input tickets while input is left, else vault
+        // tickets; once the warp holds its quota of unredeemable ones it counts as idle and looks at the termination test)
         const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < (a.n_in ? 16 : 32);
-        const int n_fill = (may_take_in || may_take_vault) ? n_load - n_wait : 0;
+        const bool input_left = a.n_in != 0ull && w_input_left != 0u;
+        const int n_fill = (input_left ? may_take_in : may_take_vault) ? n_load - n_wait : 0;
+        const int n_parked = n_cen + n_snd + n_fill;
         int type;
-        if (n_cen + n_snd + n_fill >= kService) type = (n_snd >= n_cen && n_snd >= n_fill) ? kStSend : (n_cen >= n_fill ? kStCensus : kStLoad);
+        if (n_parked >= kService) type = kStLoad;
         else if (n_col >= 32) type = kStCollision;
         else if (n_seg >= 32) type = kStSegment;
         else
         {
             type = kStSegment; int best = n_seg;
             if (n_col > best) { best = n_col; type = kStCollision; }
-            if (n_fill > best) { best = n_fill; type = kStLoad; }
-            if (n_cen > best) { best = n_cen; type = kStCensus; }
-            if (n_snd > best) { best = n_snd; type = kStSend; }
+            if (n_parked > best) { best = n_parked; type = kStLoad; }
             if (best == 0)
             {
                 // only tickets that cannot be redeemed yet: the warp is idle.  The cycle is over when no history is queued or
@@ -494,9 +499,30 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             }
         }
 
-        if (type == kStLoad)
+        if (type == kStLoad)            // the service phase: SEND, CENSUS, LOAD
         {
-            if (lane == 0 && w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
+            for (int left = n_snd; left > 0; left -= 32)
+            {
+                const int n_act = wq_send<kPeer>(a, s, warp, lane);
+                if (lane == 0) { w.n[kNSnd] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
+            }
+            for (int left = n_cen; left > 0; left -= 32)
+            {
+                const int n_act = wq_census(a, s, warp, lane);
+                if (lane == 0) { w.n[kNCen] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
+            }
+            unsigned expired = 0u;
+            if (lane == 0)
+            {
+                if (w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
+                // never hang the device, whatever state a warp is in: the watchdog is looked at in every service phase
+                if (global_timer_ns() - w.t_start > (a.watchdog_ns ? a.watchdog_ns : 20000000000ull))
+                {
+                    expired = 1u;
+                    atomicOr(&a.ctl->overflow, 8u);         // (peer mode: the service warp's own watchdog tells the other ranks)
+                }
+            }
+            if (__shfl_sync(kFullMask, expired, 0)) break;
             const WqLoaded got = wq_load(a, s, warp, lane, may_take_in, may_take_vault);
             if (lane == 0)
             {
@@ -594,32 +620,28 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStCollision || st == kStTail; });
             const bool active = lane < total;
             const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
+            // Three phases, each with only the fields it needs in registers (the rest of the particle stays in its slot): reaction
+            // and sampled outcomes (energy, random-number stream, cross sections) -- secondaries (rare; the parent's record is
+            // copied from the slot) -- outgoing trajectory (direction, census clock).
             Counters c = {};
-            Particle p;
             bool tail = false;
             double energy0 = 0.0, angle0 = 0.0, energy1 = 0.0, angle1 = 0.0, energy2 = 0.0, angle2 = 0.0, energy3 = 0.0, angle3 = 0.0;
             int n_out = 0;
+            uint64_t seed = 0;
             if (active)
             {
+                Particle p;
                 tail = s.state[slot] == kStTail;
-                p.x = s.x[slot]; p.y = s.y[slot]; p.z = s.z[slot];
-                p.alpha = s.alpha[slot]; p.beta = s.beta[slot]; p.gamma = s.gamma[slot];
-                p.energy = s.energy[slot]; p.weight = s.weight[slot]; p.ttc = s.ttc[slot]; p.age = s.age[slot];
-                p.nmfp = s.nmfp[slot]; p.nseg = s.nseg[slot]; p.speed = s.speed[slot];
-#if QSB_VALIDATION
-                p.vx = s.vx[slot]; p.vy = s.vy[slot]; p.vz = s.vz[slot];
-#endif
+                p.energy = s.energy[slot];
                 p.seed = s.seed[slot];
                 load_head(s, slot, p);
-                p.cell = s.cell[slot];
-                p.num_collisions = s.num_collisions[slot]; p.breed = s.breed[slot]; p.species = s.species[slot];
                 p.group = s.group[slot];
-                p.last_event = QSB_EV_COLLISION; p.facet = 0;
                 // the total cross section the segment ended on (MC_Segment_Outcome leaves it in the particle, src/MC_Segment_Outcome.cc:60-66)
                 p.total_xs = __ldg(a.im.xs_pair + (size_t)cell_material(p.head) * a.im.n_groups + p.group).x;
-                energy0 = p.energy; angle0 = p.nmfp;                    // a raw child carries its sampled outcome in these two fields
+                energy0 = p.energy; angle0 = s.nmfp[slot];              // a raw child carries its sampled outcome in these two fields
                 n_out = 1;
                 if (!tail) n_out = collision_head(a, p, c, energy0, angle0, energy1, angle1, energy2, angle2, energy3, angle3);
+                seed = p.seed;
             }
             // balance tallies of the batch (src/CollisionEvent.cc:104-119), from ballots: nothing per-thread stays live
             const unsigned t_col = __popc(__ballot_sync(kFullMask, c.collisions != 0u));
@@ -662,9 +684,11 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                     }
                     else
                     {
-                        write_raw_child(a, first, p, qs_rng_spawn(&p.seed), energy1, angle1);
-                        if (n_child > 1u) write_raw_child(a, first + 1, p, qs_rng_spawn(&p.seed), energy2, angle2);
-                        if (n_child > 2u) write_raw_child(a, first + 2, p, qs_rng_spawn(&p.seed), energy3, angle3);
+                        Particle parent;
+                        load_all(s, slot, parent);
+                        write_raw_child(a, first, parent, qs_rng_spawn(&seed), energy1, angle1);
+                        if (n_child > 1u) write_raw_child(a, first + 1, parent, qs_rng_spawn(&seed), energy2, angle2);
+                        if (n_child > 2u) write_raw_child(a, first + 2, parent, qs_rng_spawn(&seed), energy3, angle3);
                         s.pub_first[threadIdx.x] = first; s.pub_n[threadIdx.x] = n_child;       // published at the top of the next iteration
                     }
                 }
@@ -674,6 +698,10 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             {
                 if (n_out > 0)
                 {
+                    Particle p;
+                    p.alpha = s.alpha[slot]; p.beta = s.beta[slot]; p.gamma = s.gamma[slot];
+                    p.ttc = s.ttc[slot]; p.age = s.age[slot];
+                    p.seed = seed;
                     collision_tail(a, p, energy0, angle0, tail || n_out > 1);
                     s.energy[slot] = p.energy;
                     s.alpha[slot] = p.alpha; s.beta[slot] = p.beta; s.gamma[slot] = p.gamma;
@@ -704,17 +732,6 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             continue;
         }
 
-        if (type == kStCensus)
-        {
-            const int n_act = wq_census(a, s, warp, lane);
-            if (lane == 0) { w.n[kNCen] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
-            continue;
-        }
-
-        {
-            const int n_act = wq_send<kPeer>(a, s, warp, lane);
-            if (lane == 0) { w.n[kNSnd] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
-        }
     }
 
     // flush the warp's balance counters: one atomic per counter
