@@ -232,6 +232,7 @@ struct qsb_ctx
     size_t n_marks = 0;
     size_t n_chunks = 0;
     bool streaming = false, stream_input_issued = false;
+    bool peer_multi_domain = false;             // some rank owns more than one domain (qsb_peer_connect)
     const qsb_base_particle* host_in = nullptr;
     unsigned long long n_in_aos = 0;            // tickets [0, n_in_aos) are streamed host records this cycle
     qsb_base_particle* host_out = nullptr;
@@ -994,12 +995,13 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.check_mode = ((c->opt.tracking_mode & 2) ? 1 : 0) | ((c->opt.tracking_mode & 4) ? 2 : 0);
         a.in_aos = c->d_in_aos; a.n_in = c->n_in_aos;
         a.inflight = &c->d_ctl->inflight; a.tail = &c->d_ctl->tail;
-        a.peer_mode = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
+        a.peer_mode = 0; a.peer_multi_domain = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
         for (int r = 0; r < kMaxPeers; ++r) a.peer_base[r] = c->peer_base[r];
         if (c->peer_on)
         {
             if (c->proc != 0) { c->error = "peer exchange: the exported processing vault is vault 0 (keep_census is not supported with it)"; return (int)QSB_ERR_STATE; }
             a.peer_mode = 1;
+            a.peer_multi_domain = c->peer_multi_domain ? 1 : 0;
             a.peer_epoch = ++c->peer_epoch;
             PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
             a.inflight = &d_peer->inflight; a.tail = &d_peer->tail;
@@ -1302,12 +1304,18 @@ int qsb_peer_export(qsb_ctx* c, void* handle, uint64_t* vault_capacity)
     static_assert(kMaxPeers == QSB_MAX_PEERS, "peer limit");
     static_assert(sizeof(PeerControl) <= kVaultHeaderBytes, "vault header");
     return guarded(c, [&]() {
-        if (c->im.n_domains != 1) { c->error = "peer exchange needs one domain per rank"; return (int)QSB_ERR_STATE; }
+        if (c->im.n_domains < 1 || c->im.n_domains > kMaxDomainsPerRank)
+        { c->error = "peer exchange: at most " + std::to_string(kMaxDomainsPerRank) + " domains per rank"; return (int)QSB_ERR_STATE; }
         if (!c->peer_block)
         {
             c->peer_block = c->vault_base[0];
             QSB_CUDA(cudaMallocHost((void**)&c->h_peer, sizeof(PeerControl)));
             std::memset(c->h_peer, 0, sizeof(PeerControl));
+            // where this rank's domains start in its flat cell index space: read by depositing peers (peer_destination_cell)
+            c->h_peer->n_domains = c->im.n_domains;
+            for (int d = 0; d < c->im.n_domains; ++d) c->h_peer->domain_offset[d] = c->host_domain_offset[d];
+            PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
+            QSB_CUDA(cudaMemcpy(&d_peer->n_domains, &c->h_peer->n_domains, sizeof(int) * (1 + kMaxDomainsPerRank), cudaMemcpyHostToDevice));
         }
         cudaIpcMemHandle_t h;
         QSB_CUDA(cudaIpcGetMemHandle(&h, c->peer_block));
@@ -1340,6 +1348,16 @@ int qsb_peer_connect(qsb_ctx* c, const void* handles, int n_ranks, double watchd
                 return (int)QSB_ERR_CUDA;
             }
             c->peer_base[r] = (char*)p;
+        }
+        // does any rank own several domains?  (every rank wrote its header in qsb_peer_export, before its handle left)
+        c->peer_multi_domain = c->im.n_domains > 1;
+        for (int r = 0; r < n_ranks; ++r)
+        {
+            if (r == c->my_rank) continue;
+            int nd = 0;
+            QSB_CUDA(cudaMemcpy(&nd, &reinterpret_cast<PeerControl*>(c->peer_base[r])->n_domains, sizeof(int), cudaMemcpyDeviceToHost));
+            if (nd < 1 || nd > kMaxDomainsPerRank) { c->error = "qsb_peer_connect: rank " + std::to_string(r) + " has not exported its domain table"; return (int)QSB_ERR_STATE; }
+            if (nd > 1) c->peer_multi_domain = true;
         }
         c->watchdog_ns = (unsigned long long)((watchdog_seconds > 0 ? watchdog_seconds : 60.0) * 1e9);
         c->peer_on = std::getenv("QSB_DEBUG_PEER_MAP_ONLY") == nullptr;      // experiment: mappings in place, exchange left to the caller

@@ -131,6 +131,7 @@ struct DevControl
 // launch named by `epoch` (the host writes them, then `epoch`, in stream order before the launch; a sender waits for the
 // peer's epoch before it touches them).  Global termination is decided on the devices: peer_service_loop in track_kernels.cu.
 constexpr int kMaxPeers = 8;
+constexpr int kMaxDomainsPerRank = 64;
 struct PeerControl
 {
     unsigned long long sent;            // deposits started TOWARDS this GPU (remote atomics, while the sender still counts the history)
@@ -154,8 +155,14 @@ struct PeerControl
     unsigned long long send_calls;
     unsigned long long startup_wait_ns;
     unsigned int pad5[14];
+    // written once by qsb_peer_export: where each of this rank's domains starts in its flat cell index space (a depositing
+    // peer knows the destination as (rank-local domain, cell) and stores the flat cell, src/initMC.cc:256-259: a rank may own
+    // several domains)
+    int n_domains;
+    int domain_offset[kMaxDomainsPerRank];
+    int pad6[3];
 };
-static_assert(sizeof(PeerControl) == 1152, "PeerControl layout");
+static_assert(sizeof(PeerControl) == 1152 + 16 + 4 * kMaxDomainsPerRank, "PeerControl layout");
 constexpr size_t kVaultHeaderBytes = 2048;     // PeerControl sits at the head of the processing vault's allocation
 
 // the SoA arrays of a vault inside one allocation: 18 eight-byte arrays, tags, cell, ready (capacity is a multiple of 32)
@@ -207,6 +214,7 @@ struct TrackArgs
     // peer exchange (peer_mode != 0): base of every rank's exported allocation (own rank: the local pointer); every rank's
     // processing vault has this rank's capacity
     int peer_mode, my_rank;
+    int peer_multi_domain;              // some rank owns more than one domain: a deposit adds the destination domain's offset (read from the peer)
     uint32_t peer_epoch;
     char* peer_base[kMaxPeers];
     unsigned long long watchdog_ns;     // give up (abort everywhere) when a launch has not terminated after this long

@@ -366,7 +366,7 @@ __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned wa
                     atomicAdd_system(&pc->inflight, 0ull - 1ull);
                 }
                 else
-                    store_deposit(vault_view(a.peer_base[dest], a.proc.capacity), vslot, p, __ldg(im.face_adj_cell + k), s.launch[dest].vault_epoch);
+                    store_deposit(vault_view(a.peer_base[dest], a.proc.capacity), vslot, p, peer_destination_cell(a, pc, k), s.launch[dest].vault_epoch);
             }
             __syncwarp();
             if (lane == head_lane)

@@ -1043,6 +1043,19 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 __device__ __forceinline__ PeerControl* peer_control(const TrackArgs& a, int rank) { return reinterpret_cast<PeerControl*>(a.peer_base[rank]); }
 
+// the flat cell index, on the destination rank, of the cell behind off-rank face k = cell * 6 + face of this rank
+__device__ __forceinline__ int peer_destination_cell(const TrackArgs& a, const PeerControl* pc, size_t k)
+{
+    int cell = __ldg(a.im.face_adj_cell + k);                      // local to the neighbour's domain
+    if (a.peer_multi_domain)
+    {
+        int off;
+        asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(off) : "l"(pc->domain_offset + __ldg(a.im.face_adj_domain + k)) : "memory");
+        cell += off;
+    }
+    return cell;
+}
+
 // what a block knows about the peers' current launch (filled once per block at kernel start, see track_kernel)
 struct PeerLaunch { unsigned long long n_in; unsigned int vault_epoch; unsigned int pad; };
 
@@ -1087,7 +1100,7 @@ __device__ __forceinline__ unsigned send_advance(const TrackArgs& a, const PeerL
                 atomicAdd_system(&pc->inflight, 0ull - 1ull);
             }
             else
-                store_deposit(vault_view(a.peer_base[rank], a.proc.capacity), slot, p, __ldg(im.face_adj_cell + k), launch[rank].vault_epoch);
+                store_deposit(vault_view(a.peer_base[rank], a.proc.capacity), slot, p, peer_destination_cell(a, pc, k), launch[rank].vault_epoch);
             asm volatile("red.relaxed.sys.global.add.u64 [%0], %1;" :: "l"(&pc->received), "l"(1ull) : "memory");
             s.stage = 0;
         }

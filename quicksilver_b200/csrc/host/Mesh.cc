@@ -200,11 +200,22 @@ void initMesh(const Parameters& params, const MaterialDatabase& db, int myRank, 
     GlobalFccGrid grid(sp.nx, sp.ny, sp.nz, sp.lx, sp.ly, sp.lz);
 
     ddc.nRanks = nRanks; ddc.myRank = myRank;
-    ddc.nDomainsPerRank = (sp.xDom == 0 && sp.yDom == 0 && sp.zDom == 0 && nRanks == 1) ? 4 : 1;
+    // src/initMC.cc:256-259: four randomly centred domains on a single rank without a domain grid, else one domain per rank.
+    // Beyond the reference (which stops at `nRanks > 1 && nDomainsPerRank != 1`, src/initMC.cc:288-289): a domain grid with
+    // k * nRanks centres gives every rank k consecutive domains (north_star: "one or more domains per GPU").
+    const bool noGrid = sp.xDom == 0 && sp.yDom == 0 && sp.zDom == 0;
+    const long long gridCenters = (long long)sp.xDom * sp.yDom * sp.zDom;
+    if (noGrid) ddc.nDomainsPerRank = nRanks == 1 ? 4 : 1;
+    else
+    {
+        if (gridCenters <= 0 || gridCenters % nRanks != 0)
+            throw std::runtime_error("xDom*yDom*zDom must be a multiple of the number of ranks (GPUs)");
+        ddc.nDomainsPerRank = (int)(gridCenters / nRanks);
+    }
     const int nCenters = nRanks * ddc.nDomainsPerRank;
     domainCenters(params, grid, nCenters, ddc.centers);
     if ((int)ddc.centers.size() != nCenters)
-        throw std::runtime_error("xDom*yDom*zDom must equal the number of ranks (GPUs)");
+        throw std::runtime_error("xDom*yDom*zDom must be a multiple of the number of ranks (GPUs)");
     for (int i = 0; i < ddc.nDomainsPerRank; ++i) ddc.myDomainGids.push_back(ddc.nDomainsPerRank * myRank + i);
 
     // owner domain and domain-local index of every global cell (local index = rank by ascending gid)

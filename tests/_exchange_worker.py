@@ -35,13 +35,14 @@ def main():
                                 make_backend=lambda mc: H.OracleBackend(mc.image, mc.get_double("dt"), rank, world, strict=False))
     rows, info = [], []
     gid = sim.mc.image.array("cell_gid")
+    domain_offset = sim.mc.image.array("domain_cell_offset")      # several domains per rank: records carry (rank-local domain, cell)
     for c in range(cycles):
         row, flux, meta = sim.cycle()
         rows.append([int(v) for v in row] + [flux])
         info.append({"rounds": meta["rounds"], "sent": meta["sent"]})
         census, _, _ = sim.backend.results()
         census = census.copy()
-        census["cell"] = gid[census["cell"]]
+        census["cell"] = gid[domain_offset[census["domain"]] + census["cell"]]
         census["domain"] = 0
         np.save(os.path.join(out_dir, "census_c%d_r%d.npy" % (c, rank)), census)
     report, passed = sim.report()            # collective: timer table (min/avg/max over ranks) + FOM + CORAL self checks

@@ -41,13 +41,16 @@ def _single_rank(argv, cycles):
     return rows, censuses
 
 
-@pytest.mark.parametrize("deck_name,grid,n,per_cell", [("CTS2", (2, 1, 1), 4, 10), ("Coral2_P1", (2, 2, 1), 3, 40)])
-def test_domain_decomposed_run_equals_single_rank_run(tmp_path, deck_name, grid, n, per_cell):
+@pytest.mark.parametrize("deck_name,grid,n,per_cell,ranks", [("CTS2", (2, 1, 1), 4, 10, 2), ("Coral2_P1", (2, 2, 1), 3, 40, 4),
+                                                               ("Coral2_P1", (2, 2, 1), 3, 40, 2)])
+def test_domain_decomposed_run_equals_single_rank_run(tmp_path, deck_name, grid, n, per_cell, ranks):
+    """the last case: 4 domains on 2 ranks -- two domains per rank, which the reference stops at (src/initMC.cc:288-289) and
+    north_star asks for ("one or more domains per GPU")"""
     gx, gy, gz = grid
-    world = gx * gy * gz
+    world = ranks
     cycles = 3
     deck = decks.write_deck(decks.derive(deck_name, nSteps=cycles), str(tmp_path / "deck.inp"))
-    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * world]
+    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * gx * gy * gz]
     argv1 = [str(a) for a in ["-i", deck] + sizes + ["-I", 1, "-J", 1, "-K", 1]]
     argvN = [str(a) for a in ["-i", deck] + sizes + ["-I", gx, "-J", gy, "-K", gz]]
     want_rows, want_census = _single_rank(argv1, cycles)

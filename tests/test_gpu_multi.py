@@ -44,20 +44,21 @@ def _single_rank_strict(argv, cycles, strict_source=False):
 
 
 @pytest.mark.parametrize("exchange", ["peer", "nccl"])
-@pytest.mark.parametrize("deck_name,grid,n,per_cell", [("CTS2", (2, 1, 1), 8, 10), ("Coral2_P1", (2, 2, 1), 6, 40),
-                                                         ("Coral2_P2", (2, 2, 2), 4, 40)])
-def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_cell, exchange):
+@pytest.mark.parametrize("deck_name,grid,n,per_cell,n_ranks", [("CTS2", (2, 1, 1), 8, 10, 2), ("Coral2_P1", (2, 2, 1), 6, 40, 4),
+                                                                 ("Coral2_P2", (2, 2, 2), 4, 40, 8), ("Coral2_P1", (2, 2, 1), 6, 40, 2)])
+def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_cell, n_ranks, exchange):
     """exchange = "peer": the kernels deposit boundary particles in each other's rings over NVLink and decide termination
-    on the devices (one launch per cycle); "nccl": per-round slabs moved with NCCL send/recv."""
+    on the devices (one launch per cycle); "nccl": per-round slabs moved with NCCL send/recv.  Last case: a 2 x 2 domain grid
+    on 2 GPUs -- two domains per GPU (north_star: "one or more domains per GPU"; the reference stops there, src/initMC.cc:288-289)."""
     gx, gy, gz = grid
-    world = gx * gy * gz
+    world = n_ranks
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cycles = 3
     cell = 1.0 / 11.0 if deck_name == "Coral2_P2" else 1.0
     deck = decks.write_deck(decks.derive(deck_name, nSteps=cycles), str(tmp_path / "deck.inp"))
     sizes = ["-X", n * gx * cell, "-Y", n * gy * cell, "-Z", n * gz * cell, "-x", n * gx, "-y", n * gy, "-z", n * gz,
-             "-n", per_cell * n ** 3 * world]
+             "-n", per_cell * n ** 3 * gx * gy * gz]
     argv1 = [str(a) for a in ["-i", deck] + sizes + ["-I", 1, "-J", 1, "-K", 1]]
     argvN = [str(a) for a in ["-i", deck] + sizes + ["-I", gx, "-J", gy, "-K", gz]]
     want_rows, want_census = _single_rank_strict(argv1, cycles)
@@ -83,15 +84,16 @@ def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_c
         assert H.sort_particles(union).tobytes() == H.sort_particles(want_census[c]).tobytes(), "cycle %d census" % c
 
 
-@pytest.mark.parametrize("exchange", ["peer", "nccl"])
-def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange):
+@pytest.mark.parametrize("exchange,grid", [("peer", (2, 1, 1)), ("nccl", (2, 1, 1)), ("peer", (2, 2, 1))])
+def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange, grid):
     """the population stays on the GPUs from cycle to cycle (cycleInit on every device, split factor from the allreduced
-    global count); rows and census must equal the single-rank CPU chain -- host cycleInit in strict-math mode + oracle."""
-    world, (gx, gy, gz), n, per_cell, cycles = 2, (2, 1, 1), 8, 10, 3
+    global count); rows and census must equal the single-rank CPU chain -- host cycleInit in strict-math mode + oracle.
+    Grid (2, 2, 1) on 2 GPUs: two domains per GPU."""
+    world, (gx, gy, gz), n, per_cell, cycles = 2, grid, 8, 10, 3
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
     deck = decks.write_deck(decks.derive("CTS2", nSteps=cycles), str(tmp_path / "deck.inp"))
-    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * world]
+    sizes = ["-X", n * gx, "-Y", n * gy, "-Z", n * gz, "-x", n * gx, "-y", n * gy, "-z", n * gz, "-n", per_cell * n ** 3 * gx * gy * gz]
     argv1 = [str(a) for a in ["-i", deck] + sizes + ["-I", 1, "-J", 1, "-K", 1]]
     argvN = [str(a) for a in ["-i", deck] + sizes + ["-I", gx, "-J", gy, "-K", gz]]
     want_rows, want_census = _single_rank_strict(argv1, cycles, strict_source=True)
