@@ -110,7 +110,10 @@ __device__ __forceinline__ Decisions population_control(const CycleInitArgs& a, 
     return d;
 }
 
-__global__ void __launch_bounds__(256) cycle_init_kernel(const __grid_constant__ CycleInitArgs a)
+#ifndef QSB_CI_MIN_BLOCKS
+#define QSB_CI_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, QSB_CI_MIN_BLOCKS) cycle_init_kernel(const __grid_constant__ CycleInitArgs a)
 {
     __shared__ unsigned long long s_warp_base[8];
     __shared__ unsigned s_warp_count[8];

@@ -223,6 +223,7 @@ struct qsb_ctx
     // host-buffer streaming (qsb_stream_begin / qsb_track / qsb_stream_end, see include/qsb.h)
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     cudaEvent_t ev_ctl = nullptr, ev_stage[2] = { nullptr, nullptr };
+    cudaEvent_t ev_in_done = nullptr;           // QSB_TRACE: the last input chunk of a streamed cycle has landed (timed against ev0)
     qsb_base_particle* d_in_aos = nullptr;      size_t in_aos_cap = 0;
     qsb_base_particle* d_census_aos = nullptr;  // [vault capacity]
     unsigned int* d_chunk_done = nullptr;       // [n_chunks]
@@ -356,6 +357,7 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
         QSB_CUDA(cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking));
         QSB_CUDA(cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking));
         QSB_CUDA(cudaEventCreateWithFlags(&c->ev_ctl, cudaEventDisableTiming));
+        QSB_CUDA(cudaEventCreate(&c->ev_in_done));
         QSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[0], cudaEventDisableTiming));
         QSB_CUDA(cudaEventCreateWithFlags(&c->ev_stage[1], cudaEventDisableTiming));
 
@@ -616,6 +618,7 @@ int qsb_destroy(qsb_ctx* c)
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
     if (c->stream_out) cudaStreamDestroy(c->stream_out);
     if (c->ev_ctl) cudaEventDestroy(c->ev_ctl);
+    if (c->ev_in_done) cudaEventDestroy(c->ev_in_done);
     for (cudaEvent_t e : c->ev_stage) if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -899,6 +902,7 @@ void issueStreamInput(qsb_ctx* c)
         QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->in_ready, &c->h_marks[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream_in));
         if (!pinned) serviceCensus(c, false);
     }
+    QSB_CUDA(cudaEventRecord(c->ev_in_done, c->stream_in));
 }
 
 // start the D2H copy of every census chunk the kernel has announced (final = false), or of everything that is left
@@ -1143,9 +1147,16 @@ int qsb_stream_end(qsb_ctx* c, uint64_t* n_census)
         QSB_CUDA(cudaStreamSynchronize(c->stream_out));
         QSB_CUDA(cudaStreamSynchronize(c->stream_in));
         if (trace)
-            std::fprintf(stderr, "[qsb] stream_end: %llu of %llu census records were left to copy, %.2f ms\n",
+        {
+            float in_ms = 0.f, k_ms = 0.f;
+            if (c->n_in_aos && cudaEventElapsedTime(&in_ms, c->ev0, c->ev_in_done) != cudaSuccess) { cudaGetLastError(); in_ms = -1.f; }
+            if (cudaEventElapsedTime(&k_ms, c->ev0, c->ev1) != cudaSuccess) { cudaGetLastError(); k_ms = -1.f; }
+            std::fprintf(stderr, "[qsb] stream_end: %llu of %llu census records were left to copy, %.2f ms; last input chunk landed %.2f ms after the "
+                         "kernel's start (%.1f GB/s), kernel ended after %.2f ms\n",
                          (unsigned long long)*n_census - before, (unsigned long long)*n_census,
-                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), in_ms,
+                         in_ms > 0 ? c->n_in_aos * sizeof(qsb_base_particle) / (in_ms * 1e6) : 0.0, k_ms);
+        }
         return (int)QSB_OK;
     });
 }

@@ -123,6 +123,9 @@ constexpr int kWqK = (kWq + 31) / 32;               // ... per lane of bookkeepi
 constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
+#ifndef QSB_OPT_SERVICE_ALL
+#define QSB_OPT_SERVICE_ALL 0           // 1: a service phase always does everything (send, census, refill); 0: sends + the larger of census / refill
+#endif
 #ifndef QSB_WQ_SERVICE
 #define QSB_WQ_SERVICE (QSB_WQ_SLOTS_PER_WARP / 2)
 #endif
@@ -462,14 +465,26 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         const int n_fill = (input_left ? may_take_in : may_take_vault) ? n_load - n_wait : 0;
         const int n_parked = n_cen + n_snd + n_fill;
         int type;
+#if QSB_OPT_SERVICE_ALL
+        bool do_census = true, do_load = true;
         if (n_parked >= kService) type = kStLoad;
+#else
+        // which of the services: the one with most slots waiting (sends ride along with either, see below)
+        bool do_census = n_cen + n_snd >= n_fill, do_load = !do_census;
+        if (n_parked >= kService) type = kStLoad;
+#endif
         else if (n_col >= 32) type = kStCollision;
         else if (n_seg >= 32) type = kStSegment;
         else
         {
             type = kStSegment; int best = n_seg;
             if (n_col > best) { best = n_col; type = kStCollision; }
+#if QSB_OPT_SERVICE_ALL
             if (n_parked > best) { best = n_parked; type = kStLoad; }
+#else
+            if (n_fill > best) { best = n_fill; type = kStLoad; do_load = true; do_census = false; }
+            if (n_cen + n_snd > best) { best = n_cen + n_snd; type = kStLoad; do_census = true; do_load = false; }
+#endif
             if (best == 0)
             {
                 // only tickets that cannot be redeemed yet: the warp is idle.  The cycle is over when no history is queued or
@@ -495,7 +510,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                 }
                 if (__shfl_sync(kFullMask, done, 0)) break;
                 __nanosleep(__shfl_sync(kFullMask, backoff, 0));
-                type = kStLoad;
+                type = kStLoad; do_load = true; do_census = false;
             }
         }
 
@@ -506,11 +521,12 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                 const int n_act = wq_send<kPeer>(a, s, warp, lane);
                 if (lane == 0) { w.n[kNSnd] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
             }
-            for (int left = n_cen; left > 0; left -= 32)
+            for (int left = do_census ? n_cen : 0; left > 0; left -= 32)
             {
                 const int n_act = wq_census(a, s, warp, lane);
                 if (lane == 0) { w.n[kNCen] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
             }
+            if (!do_load) continue;
             unsigned expired = 0u;
             if (lane == 0)
             {
