@@ -233,6 +233,7 @@ struct qsb_ctx
     size_t n_marks = 0;
     size_t n_chunks = 0;
     bool streaming = false, stream_input_issued = false;
+    uint32_t arr_epoch = 0xffffffffu;           // cycle (vault epoch) the arrival region was last emptied for
     bool peer_multi_domain = false;             // some rank owns more than one domain (qsb_peer_connect)
     const qsb_base_particle* host_in = nullptr;
     unsigned long long n_in_aos = 0;            // tickets [0, n_in_aos) are streamed host records this cycle
@@ -999,13 +1000,22 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.check_mode = ((c->opt.tracking_mode & 2) ? 1 : 0) | ((c->opt.tracking_mode & 4) ? 2 : 0);
         a.in_aos = c->d_in_aos; a.n_in = c->n_in_aos;
         a.inflight = &c->d_ctl->inflight; a.tail = &c->d_ctl->tail;
-        a.peer_mode = 0; a.peer_multi_domain = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
+        a.peer_mode = 0; a.peer_multi_domain = 0; a.arrival_first = 0; a.arrival_cap = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
         for (int r = 0; r < kMaxPeers; ++r) a.peer_base[r] = c->peer_base[r];
         if (c->peer_on)
         {
             if (c->proc != 0) { c->error = "peer exchange: the exported processing vault is vault 0 (keep_census is not supported with it)"; return (int)QSB_ERR_STATE; }
             a.peer_mode = 1;
             a.peer_multi_domain = c->peer_multi_domain ? 1 : 0;
+#if QSB_OPT_ARRIVAL_QUEUE
+            if (c->event_mode)
+            {
+                a.arrival_cap = a.proc.capacity / 8;
+                a.arrival_first = a.proc.capacity - a.arrival_cap;
+                if (c->h_ctl->tail - c->n_in_aos > a.arrival_first)
+                { c->error = "peer exchange: the processing vault's population reaches into the arrival region (the last eighth of particle_capacity); raise qsb_options.particle_capacity"; return (int)QSB_ERR_CAPACITY; }
+            }
+#endif
             a.peer_epoch = ++c->peer_epoch;
             PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
             a.inflight = &d_peer->inflight; a.tail = &d_peer->tail;
@@ -1033,6 +1043,13 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             PeerControl* d_peer = reinterpret_cast<PeerControl*>(c->peer_block);
             c->h_peer->inflight = c->h_ctl->inflight;
             c->h_peer->tail = c->h_ctl->tail;
+            // the arrival region: emptied with the first launch of a cycle (slots are stamped with the cycle's epoch); a later
+            // launch of the same cycle goes on where the last one stopped -- slots claimed past the tail by warps that are gone
+            // were never redeemed
+            if (c->arr_epoch != c->epoch) { c->arr_epoch = c->epoch; c->h_peer->arr_tail = 0; c->h_ctl->arr_head = 0; }
+            else c->h_ctl->arr_head = std::min(c->h_ctl->arr_head, c->h_peer->arr_tail);
+            QSB_CUDA(cudaMemcpyAsync(&d_peer->arr_tail, &c->h_peer->arr_tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            QSB_CUDA(cudaMemcpyAsync(&c->d_ctl->arr_head, &c->h_ctl->arr_head, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
             c->h_peer->n_in = c->n_in_aos;
             c->h_peer->vault_epoch = c->epoch;
             c->h_peer->epoch = c->peer_epoch;

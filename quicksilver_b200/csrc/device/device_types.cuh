@@ -110,6 +110,8 @@ struct DevControl
     unsigned long long pad4[31];
     unsigned long long head_in;         // event kernel, host-buffer streaming: next unclaimed ticket of the INPUT queue [0, n_in); `head` then
     unsigned long long pad5[31];        // serves the vault slots only (tickets >= n_in), so secondaries do not queue behind the whole input
+    unsigned long long arr_head;        // event kernel, peer mode: next unclaimed slot of the arrival region (its tail: PeerControl::arr_tail)
+    unsigned long long pad6[31];
     unsigned long long slow_geometry;   // segments that took the full 24-facet path
     unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];
@@ -131,6 +133,15 @@ struct DevControl
 // launch named by `epoch` (the host writes them, then `epoch`, in stream order before the launch; a sender waits for the
 // peer's epoch before it touches them).  Global termination is decided on the devices: peer_service_loop in track_kernels.cu.
 constexpr int kMaxPeers = 8;
+// Event kernel, peer mode: particles deposited by other GPUs do not queue behind this GPU's own population and secondaries
+// (one FIFO made every hop of a particle that crosses back and forth wait for the bulk of the cycle, and the chains of hops
+// then ran one after the other on nearly empty GPUs at the end).  They get a region of their own at the top of the
+// processing vault -- the last capacity / 8 slots -- with its own tail (PeerControl::arr_tail, raised by the senders) and
+// head (DevControl::arr_head), and LOAD serves it first.  An arrival's ticket is its slot number in the region + kArrivalTicket.
+#ifndef QSB_OPT_ARRIVAL_QUEUE
+#define QSB_OPT_ARRIVAL_QUEUE 1
+#endif
+constexpr unsigned long long kArrivalTicket = 1ull << 62;
 constexpr int kMaxDomainsPerRank = 64;
 struct PeerControl
 {
@@ -140,8 +151,10 @@ struct PeerControl
     unsigned long long pad1[31];
     unsigned long long inflight;        // histories queued or running on this GPU (the kernel's in-flight counter in peer mode)
     unsigned long long pad2[31];
-    unsigned long long tail;            // tickets allocated (the kernel's queue tail in peer mode; remote senders add to it)
+    unsigned long long tail;            // tickets allocated (the kernel's queue tail in peer mode; history kernel: remote senders add to it)
     unsigned long long pad3[31];
+    unsigned long long arr_tail;        // event kernel: slots of the ARRIVAL region handed out to depositing peers this cycle (remote atomics)
+    unsigned long long pad3b[31];
     unsigned long long n_in;            // this launch: tickets below n_in are streamed host records, SoA slot = ticket - n_in
     unsigned int vault_epoch;           // this launch: value of a slot's ready word once it is fully written
     unsigned int epoch;                 // number of the peer-mode launch the words above belong to
@@ -162,7 +175,7 @@ struct PeerControl
     int domain_offset[kMaxDomainsPerRank];
     int pad6[3];
 };
-static_assert(sizeof(PeerControl) == 1152 + 16 + 4 * kMaxDomainsPerRank, "PeerControl layout");
+static_assert(sizeof(PeerControl) == 1152 + 256 + 16 + 4 * kMaxDomainsPerRank, "PeerControl layout");
 constexpr size_t kVaultHeaderBytes = 2048;     // PeerControl sits at the head of the processing vault's allocation
 
 // the SoA arrays of a vault inside one allocation: 18 eight-byte arrays, tags, cell, ready (capacity is a multiple of 32)
@@ -215,6 +228,7 @@ struct TrackArgs
     // processing vault has this rank's capacity
     int peer_mode, my_rank;
     int peer_multi_domain;              // some rank owns more than one domain: a deposit adds the destination domain's offset (read from the peer)
+    unsigned long long arrival_first, arrival_cap;  // the arrival region [arrival_first, arrival_first + arrival_cap) of every rank's vault (0: none)
     uint32_t peer_epoch;
     char* peer_base[kMaxPeers];
     unsigned long long watchdog_ns;     // give up (abort everywhere) when a launch has not terminated after this long

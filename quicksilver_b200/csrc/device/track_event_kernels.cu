@@ -123,6 +123,9 @@ constexpr int kWqK = (kWq + 31) / 32;               // ... per lane of bookkeepi
 constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
+#ifndef QSB_OPT_SERVICE_WATCHDOG
+#define QSB_OPT_SERVICE_WATCHDOG 1
+#endif
 #ifndef QSB_OPT_SERVICE_ALL
 #define QSB_OPT_SERVICE_ALL 0           // 1: a service phase always does everything (send, census, refill); 0: sends + the larger of census / refill
 #endif
@@ -139,7 +142,7 @@ enum { kStLoad = 0, kStSegment, kStCollision, kStTail, kStCensus, kStSend };
 // budget goes, and anything that stays live across it is spilled to local memory (measured: the spilled per-thread balance
 // counters and slot counts alone were 15 % of all stall samples).  Everybody reads it at the top of an iteration (one
 // broadcast load each), lane 0 updates it at the end of a batch.
-enum { kNSeg = 0, kNCol, kNCen, kNSnd, kNLoad, kNWait, kNWaitVault, kNCounts };
+enum { kNSeg = 0, kNCol, kNCen, kNSnd, kNLoad, kNWait, kNWaitVault, kNWaitArr, kNCounts };
 struct WqWarpState
 {
     int n[kNCounts];                // slots per state; kNWait / kNWaitVault: input / vault tickets held that could not be redeemed at the last LOAD
@@ -147,9 +150,12 @@ struct WqWarpState
     unsigned backoff;
     unsigned has_pub;               // some lane wrote fission secondaries in the last collision batch (pub_first / pub_n): publish them
     unsigned input_left;            // streamed input records may still be unclaimed (cleared once the input queue is seen empty)
+    unsigned dry;                   // > 0: the last LOAD found nothing for some empty slots; counts down the batches until the next try
+    unsigned pad;
     unsigned tally[12];             // the warp's balance counters (kTal*), flushed once at kernel end
     unsigned long long in_seen;     // host-buffer streaming: last value of ctl->in_ready the warp has seen
     unsigned long long t_start;
+    long long c_start;              // clock64() at kernel start (the service-phase watchdog)
 };
 
 struct WqShared : SlotStore<kWqSlots>
@@ -195,19 +201,25 @@ __device__ __forceinline__ unsigned wq_gather(WqShared& s, unsigned warp, unsign
 // input tickets for the rest of its empty slots; an input ticket is always redeemed eventually (the DMA front moves on its
 // own), a vault ticket past the final tail never is -- harmless, the cycle ends on the in-flight count -- and the few of
 // them a race can leave a warp with (two warps reading the same tail) are bounded by `may_take_vault`.
-struct WqLoaded { int to_segment, to_tail, waiting_in, waiting_vault; };
+//
+// Peer mode (arrival_cap != 0): a third queue, served first -- the arrival region other GPUs deposit into (device_types.cuh).
+// There, too, vault tickets are only taken for slots that exist: a warp must keep empty slots for what the peers send it.
+// `unserved` counts empty slots that found nothing to take; the scheduler then leaves the warp's refills alone for a few
+// batches (WqWarpState::dry) instead of spinning on them -- an idle warp falls through to the termination test at once.
+struct WqLoaded { int to_segment, to_tail, waiting_in, waiting_vault, waiting_arr, unserved; };
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault)
+__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault,
+                                         bool may_take_arr)
 {
     const unsigned base = warp * kWq;
     unsigned long long in_seen = s.w[warp].in_seen;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStLoad; });
-    WqLoaded out = { 0, 0, 0, 0 };
+    WqLoaded out = { 0, 0, 0, 0, 0, 0 };
     for (unsigned first = 0; first < total; first += 32u)
     {
         const bool active = first + lane < total;
@@ -217,51 +229,69 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         const unsigned want_mask = __ballot_sync(kFullMask, want);
         if (want_mask)
         {
-            const unsigned n_want = __popc(want_mask);
-            unsigned long long tb_v = 0, tb_in = 0;
-            unsigned k_v = 0, k_in = 0;
+            unsigned n_want = __popc(want_mask);
+            unsigned long long tb_v = 0, tb_in = 0, tb_a = 0;
+            unsigned k_v = 0, k_in = 0, k_a = 0;
             const unsigned leader = __ffs(want_mask) - 1;
             if (lane == leader)
             {
-                const bool input_left = a.n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < a.n_in;
-                if (input_left)
+                if (a.arrival_cap != 0ull && may_take_arr)         // peer mode: particles other GPUs have deposited come first
                 {
-                    if (may_take_vault)
+                    const unsigned long long t = ld_relaxed_u64(&peer_control(a, a.my_rank)->arr_tail), h = ld_relaxed_u64(&a.ctl->arr_head);
+                    k_a = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
+                    if (k_a) { tb_a = atomicAdd(&a.ctl->arr_head, (unsigned long long)k_a); n_want -= k_a; }
+                }
+                const bool input_left = a.n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < a.n_in;
+                if (!input_left) s.w[warp].input_left = 0u;
+                if (input_left || a.arrival_cap != 0ull)           // vault tickets only for slots that exist
+                {
+                    if (may_take_vault && n_want)
                     {
                         const unsigned long long t = ld_relaxed_u64(a.tail), h = ld_relaxed_u64(&a.ctl->head);
                         k_v = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
                     }
-                    if (may_take_in) k_in = n_want - k_v;
+                    if (input_left && may_take_in) k_in = n_want - k_v;
                 }
-                else
-                {
-                    s.w[warp].input_left = 0u;
-                    k_v = may_take_vault ? n_want : 0u;
-                }
+                else k_v = may_take_vault ? n_want : 0u;
                 if (k_v) tb_v = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
                 if (k_in) tb_in = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
             }
             tb_v = __shfl_sync(kFullMask, tb_v, leader); tb_in = __shfl_sync(kFullMask, tb_in, leader);
             k_v = __shfl_sync(kFullMask, k_v, leader); k_in = __shfl_sync(kFullMask, k_in, leader);
+            if (a.arrival_cap != 0ull) { tb_a = __shfl_sync(kFullMask, tb_a, leader); k_a = __shfl_sync(kFullMask, k_a, leader); }
             if (want)
             {
-                const unsigned r = __popc(want_mask & ((1u << lane) - 1u));
-                if (r < k_v) ticket = tb_v + r;
+                unsigned r = __popc(want_mask & ((1u << lane) - 1u));
+                if (r < k_a) ticket = kArrivalTicket + tb_a + r;
+                else if ((r -= k_a) < k_v) ticket = tb_v + r;
                 else if (r - k_v < k_in && tb_in + (r - k_v) < a.n_in) ticket = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
             }
         }
         bool ready = false;
+        unsigned long long vslot_of = 0;                // vault slot of a non-input ticket
         if (active && ticket != kNoTicket)
         {
-            if (ticket < a.n_in)
+            if (ticket >= kArrivalTicket)
+            {
+                const unsigned long long t = ticket - kArrivalTicket;
+                if (t < a.arrival_cap)
+                {
+                    vslot_of = a.arrival_first + t;
+                    uint32_t flag;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + vslot_of) : "memory");
+                    ready = flag == (a.epoch | kArrivalBit) && deposit_complete(a.proc, vslot_of, a.epoch);
+                }
+            }
+            else if (ticket < a.n_in)
             {
                 if (ticket >= in_seen)
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(in_seen) : "l"(&a.ctl->in_ready) : "memory");
                 ready = ticket < in_seen;
             }
-            else if (ticket - a.n_in < a.proc.capacity)
+            else if (ticket - a.n_in < a.proc.capacity - a.arrival_cap)
             {
                 const unsigned long long vslot = ticket - a.n_in;
+                vslot_of = vslot;
                 ready = vslot < a.ready_prefix;
                 if (!ready)
                 {
@@ -277,7 +307,7 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         {
             Particle p;
             if (ticket < a.n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
-            else state = load_particle(a, ticket - a.n_in, p);
+            else state = load_particle(a, vslot_of, p);
             store_all(s, slot, p);
             s.state[slot] = (unsigned char)(state == kStateTail ? kStTail : kStSegment);
         }
@@ -285,7 +315,9 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         out.to_segment += __popc(__ballot_sync(kFullMask, state == kStateSegment));
         out.to_tail += __popc(__ballot_sync(kFullMask, state == kStateTail));
         out.waiting_in += __popc(__ballot_sync(kFullMask, active && !ready && ticket < a.n_in));
-        out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket != kNoTicket && ticket >= a.n_in));
+        out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= a.n_in && ticket < kArrivalTicket));
+        if (a.arrival_cap != 0ull) out.waiting_arr += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= kArrivalTicket && ticket != kNoTicket));
+        out.unserved += __popc(__ballot_sync(kFullMask, active && ticket == kNoTicket));
     }
     // keep the highest DMA front any lane has seen
 #pragma unroll
@@ -356,13 +388,22 @@ __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned wa
                 atomicAdd(&a.ctl->send_count[dest], (unsigned long long)n);          // statistics only
                 dep = atomicAdd_system(&pc->sent, (unsigned long long)n);
                 dep2 = atomicAdd_system(&pc->inflight, (unsigned long long)n);
+#if QSB_OPT_ARRIVAL_QUEUE
+                ticket0 = atomicAdd_system(&pc->arr_tail, (unsigned long long)n);
+#else
                 ticket0 = atomicAdd_system(&pc->tail, (unsigned long long)n);
+#endif
                 asm volatile("" :: "l"(dep), "l"(dep2) : "memory");                 // performed: their values are here
             }
             ticket0 = __shfl_sync(kFullMask, ticket0, head_lane);
             if (active && rank == dest)
             {
+#if QSB_OPT_ARRIVAL_QUEUE
+                const unsigned long long t_arr = ticket0 + __popc(group & ((1u << lane) - 1u));
+                const unsigned long long vslot = t_arr < a.arrival_cap ? a.arrival_first + t_arr : a.proc.capacity;
+#else
                 const unsigned long long vslot = ticket0 + __popc(group & ((1u << lane) - 1u)) - s.launch[dest].n_in;
+#endif
                 if (vslot >= a.proc.capacity)
                 {
                     st_release_sys(&pc->overflow, a.peer_epoch);                     // the peer's host reports it; the particle is dropped
@@ -429,9 +470,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         WqWarpState& w0 = s.w[warp];
         for (int k = 0; k < kNCounts; ++k) w0.n[k] = 0;
         w0.n[kNLoad] = kWq;
-        w0.retired = 0u; w0.backoff = 64u; w0.has_pub = 0u; w0.input_left = 1u;
+        w0.retired = 0u; w0.backoff = 64u; w0.has_pub = 0u; w0.input_left = 1u; w0.dry = 0u; w0.pad = 0u;
         for (int k = 0; k < 12; ++k) w0.tally[k] = 0u;
-        w0.in_seen = 0ull; w0.t_start = global_timer_ns();
+        w0.in_seen = 0ull; w0.t_start = global_timer_ns(); w0.c_start = clock64();
     }
 
     for (;;)
@@ -439,9 +480,10 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         __syncwarp();
         WqWarpState& w = s.w[warp];
         const int n_seg = w.n[kNSeg], n_col = w.n[kNCol], n_cen = w.n[kNCen], n_snd = w.n[kNSnd], n_load = w.n[kNLoad];
-        const int n_wait_in = w.n[kNWait], n_wait_vault = w.n[kNWaitVault], n_wait = n_wait_in + n_wait_vault;
-        const unsigned has_pub = w.has_pub, w_input_left = w.input_left;
+        const int n_wait_in = w.n[kNWait], n_wait_vault = w.n[kNWaitVault], n_wait_arr = w.n[kNWaitArr], n_wait = n_wait_in + n_wait_vault + n_wait_arr;
+        const unsigned has_pub = w.has_pub, w_input_left = w.input_left, w_dry = w.dry;
         __syncwarp();                                   // everybody has read the state before lane 0 may change it
+        if (w_dry && lane == 0) w.dry = w_dry - 1u;
         if (has_pub)
         {
             const unsigned pub_n = s.pub_n[threadIdx.x];
@@ -460,9 +502,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         // tickets of a queue are handed out in order: holding unredeemable ones means its end (DMA front / tail) is reached
         // (n_fill: empty slots a LOAD can be expected to give a ticket to -- input tickets while input is left, else vault
         // tickets; once the warp holds its quota of unredeemable ones it counts as idle and looks at the termination test)
-        const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < (a.n_in ? 16 : 32);
+        const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < (a.n_in ? 16 : 32), may_take_arr = n_wait_arr < 32;
         const bool input_left = a.n_in != 0ull && w_input_left != 0u;
-        const int n_fill = (input_left ? may_take_in : may_take_vault) ? n_load - n_wait : 0;
+        const int n_fill = ((input_left ? may_take_in : may_take_vault) && w_dry == 0u) ? n_load - n_wait : 0;
         const int n_parked = n_cen + n_snd + n_fill;
         int type;
 #if QSB_OPT_SERVICE_ALL
@@ -531,19 +573,25 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             if (lane == 0)
             {
                 if (w.retired) { atomicAdd(a.inflight, 0ull - (unsigned long long)w.retired); w.retired = 0u; }
-                // never hang the device, whatever state a warp is in: the watchdog is looked at in every service phase
-                if (global_timer_ns() - w.t_start > (a.watchdog_ns ? a.watchdog_ns : 20000000000ull))
+                // never hang the device, whatever state a warp is in: the watchdog is looked at in every service phase (the SM's
+                // cycle counter, ~2 per ns: reading %globaltimer here, a few hundred times per warp and cycle, is not free)
+#if QSB_OPT_SERVICE_WATCHDOG
+                if ((unsigned long long)(clock64() - w.c_start) > 2ull * (a.watchdog_ns ? a.watchdog_ns : 20000000000ull))
+#else
+                if (false)
+#endif
                 {
                     expired = 1u;
                     atomicOr(&a.ctl->overflow, 8u);         // (peer mode: the service warp's own watchdog tells the other ranks)
                 }
             }
             if (__shfl_sync(kFullMask, expired, 0)) break;
-            const WqLoaded got = wq_load(a, s, warp, lane, may_take_in, may_take_vault);
+            const WqLoaded got = wq_load(a, s, warp, lane, may_take_in, may_take_vault, may_take_arr);
             if (lane == 0)
             {
                 w.n[kNSeg] += got.to_segment; w.n[kNCol] += got.to_tail; w.n[kNLoad] -= got.to_segment + got.to_tail;
-                w.n[kNWait] = got.waiting_in; w.n[kNWaitVault] = got.waiting_vault;
+                w.n[kNWait] = got.waiting_in; w.n[kNWaitVault] = got.waiting_vault; w.n[kNWaitArr] = got.waiting_arr;
+                w.dry = got.unserved ? 8u : 0u;
                 if (got.to_segment | got.to_tail) w.backoff = 64u;
             }
             continue;
@@ -693,7 +741,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                 if (n_child)
                 {
                     const unsigned long long first = cb + (incl - n_child);
-                    if (first + n_child > a.proc.capacity)
+                    if (first + n_child > a.proc.capacity - a.arrival_cap)
                     {
                         atomicOr(&a.ctl->overflow, 1u);
                         atomicAdd(a.inflight, 0ull - (unsigned long long)n_child);
