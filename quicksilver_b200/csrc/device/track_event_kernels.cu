@@ -213,9 +213,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+// kPeer / kStream: the instance carries the arrival queue / the streamed-input queue; the resident single-GPU instance has
+// neither (the tracking loop is instruction-cache bound: every instruction the refill path does not need is paid for in the
+// SEGMENT and COLLISION batches, measured)
+template <int kPeer, int kStream>
 __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault,
                                          bool may_take_arr)
 {
+    const bool has_arrivals = kPeer && a.arrival_cap != 0ull;
+    const unsigned long long n_in = kStream ? a.n_in : 0ull;
     const unsigned base = warp * kWq;
     unsigned long long in_seen = s.w[warp].in_seen;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStLoad; });
@@ -235,15 +241,15 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
             const unsigned leader = __ffs(want_mask) - 1;
             if (lane == leader)
             {
-                if (a.arrival_cap != 0ull && may_take_arr)         // peer mode: particles other GPUs have deposited come first
+                if (has_arrivals && may_take_arr)         // peer mode: particles other GPUs have deposited come first
                 {
                     const unsigned long long t = ld_relaxed_u64(&peer_control(a, a.my_rank)->arr_tail), h = ld_relaxed_u64(&a.ctl->arr_head);
                     k_a = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
                     if (k_a) { tb_a = atomicAdd(&a.ctl->arr_head, (unsigned long long)k_a); n_want -= k_a; }
                 }
-                const bool input_left = a.n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < a.n_in;
-                if (!input_left) s.w[warp].input_left = 0u;
-                if (input_left || a.arrival_cap != 0ull)           // vault tickets only for slots that exist
+                const bool input_left = kStream && n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < n_in;
+                if (kStream && !input_left) s.w[warp].input_left = 0u;
+                if (input_left || has_arrivals)                    // vault tickets only for slots that exist
                 {
                     if (may_take_vault && n_want)
                     {
@@ -254,24 +260,24 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
                 }
                 else k_v = may_take_vault ? n_want : 0u;
                 if (k_v) tb_v = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
-                if (k_in) tb_in = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
+                if (kStream && k_in) tb_in = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
             }
-            tb_v = __shfl_sync(kFullMask, tb_v, leader); tb_in = __shfl_sync(kFullMask, tb_in, leader);
-            k_v = __shfl_sync(kFullMask, k_v, leader); k_in = __shfl_sync(kFullMask, k_in, leader);
-            if (a.arrival_cap != 0ull) { tb_a = __shfl_sync(kFullMask, tb_a, leader); k_a = __shfl_sync(kFullMask, k_a, leader); }
+            tb_v = __shfl_sync(kFullMask, tb_v, leader); k_v = __shfl_sync(kFullMask, k_v, leader);
+            if (kStream) { tb_in = __shfl_sync(kFullMask, tb_in, leader); k_in = __shfl_sync(kFullMask, k_in, leader); }
+            if (has_arrivals) { tb_a = __shfl_sync(kFullMask, tb_a, leader); k_a = __shfl_sync(kFullMask, k_a, leader); }
             if (want)
             {
                 unsigned r = __popc(want_mask & ((1u << lane) - 1u));
                 if (r < k_a) ticket = kArrivalTicket + tb_a + r;
                 else if ((r -= k_a) < k_v) ticket = tb_v + r;
-                else if (r - k_v < k_in && tb_in + (r - k_v) < a.n_in) ticket = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
+                else if (kStream && r - k_v < k_in && tb_in + (r - k_v) < n_in) ticket = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
             }
         }
         bool ready = false;
         unsigned long long vslot_of = 0;                // vault slot of a non-input ticket
         if (active && ticket != kNoTicket)
         {
-            if (ticket >= kArrivalTicket)
+            if (kPeer && ticket >= kArrivalTicket)
             {
                 const unsigned long long t = ticket - kArrivalTicket;
                 if (t < a.arrival_cap)
@@ -282,15 +288,15 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
                     ready = flag == (a.epoch | kArrivalBit) && deposit_complete(a.proc, vslot_of, a.epoch);
                 }
             }
-            else if (ticket < a.n_in)
+            else if (kStream && ticket < n_in)
             {
                 if (ticket >= in_seen)
                     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(in_seen) : "l"(&a.ctl->in_ready) : "memory");
                 ready = ticket < in_seen;
             }
-            else if (ticket - a.n_in < a.proc.capacity - a.arrival_cap)
+            else if (ticket - n_in < a.proc.capacity - (kPeer ? a.arrival_cap : 0ull))
             {
-                const unsigned long long vslot = ticket - a.n_in;
+                const unsigned long long vslot = ticket - n_in;
                 vslot_of = vslot;
                 ready = vslot < a.ready_prefix;
                 if (!ready)
@@ -298,7 +304,7 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
                     uint32_t flag;
                     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + vslot) : "memory");
                     ready = flag == a.epoch;
-                    if (__builtin_expect(flag == (a.epoch | kArrivalBit), 0)) ready = deposit_complete(a.proc, vslot, a.epoch);
+                    if (kPeer && !QSB_OPT_ARRIVAL_QUEUE && __builtin_expect(flag == (a.epoch | kArrivalBit), 0)) ready = deposit_complete(a.proc, vslot, a.epoch);
                 }
             }
         }
@@ -306,7 +312,7 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         if (ready)
         {
             Particle p;
-            if (ticket < a.n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
+            if (kStream && ticket < n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
             else state = load_particle(a, vslot_of, p);
             store_all(s, slot, p);
             s.state[slot] = (unsigned char)(state == kStateTail ? kStTail : kStSegment);
@@ -314,15 +320,17 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         else if (active) s.id[slot] = ticket;
         out.to_segment += __popc(__ballot_sync(kFullMask, state == kStateSegment));
         out.to_tail += __popc(__ballot_sync(kFullMask, state == kStateTail));
-        out.waiting_in += __popc(__ballot_sync(kFullMask, active && !ready && ticket < a.n_in));
-        out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= a.n_in && ticket < kArrivalTicket));
-        if (a.arrival_cap != 0ull) out.waiting_arr += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= kArrivalTicket && ticket != kNoTicket));
+        if (kStream) out.waiting_in += __popc(__ballot_sync(kFullMask, active && !ready && ticket < n_in));
+        out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= n_in && ticket < kArrivalTicket));
+        if (has_arrivals) out.waiting_arr += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= kArrivalTicket && ticket != kNoTicket));
         out.unserved += __popc(__ballot_sync(kFullMask, active && ticket == kNoTicket));
     }
-    // keep the highest DMA front any lane has seen
+    if (kStream)            // keep the highest DMA front any lane has seen
+    {
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(kFullMask, in_seen, d); in_seen = o > in_seen ? o : in_seen; }
-    if (lane == 0) s.w[warp].in_seen = in_seen;
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(kFullMask, in_seen, d); in_seen = o > in_seen ? o : in_seen; }
+        if (lane == 0) s.w[warp].in_seen = in_seen;
+    }
     return out;
 }
 
@@ -427,7 +435,7 @@ __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned wa
     return (int)min(total, 32u);
 }
 
-template <int kDummy, int kPeer>
+template <int kDummy, int kPeer, int kStream>
 __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_kernel(const __grid_constant__ TrackArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -502,8 +510,8 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         // tickets of a queue are handed out in order: holding unredeemable ones means its end (DMA front / tail) is reached
         // (n_fill: empty slots a LOAD can be expected to give a ticket to -- input tickets while input is left, else vault
         // tickets; once the warp holds its quota of unredeemable ones it counts as idle and looks at the termination test)
-        const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < (a.n_in ? 16 : 32), may_take_arr = n_wait_arr < 32;
-        const bool input_left = a.n_in != 0ull && w_input_left != 0u;
+        const bool may_take_in = n_wait_in < 32, may_take_vault = n_wait_vault < ((kStream && a.n_in) ? 16 : 32), may_take_arr = n_wait_arr < 32;
+        const bool input_left = kStream && a.n_in != 0ull && w_input_left != 0u;
         const int n_fill = ((input_left ? may_take_in : may_take_vault) && w_dry == 0u) ? n_load - n_wait : 0;
         const int n_parked = n_cen + n_snd + n_fill;
         int type;
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                 }
             }
             if (__shfl_sync(kFullMask, expired, 0)) break;
-            const WqLoaded got = wq_load(a, s, warp, lane, may_take_in, may_take_vault, may_take_arr);
+            const WqLoaded got = wq_load<kPeer, kStream>(a, s, warp, lane, may_take_in, may_take_vault, may_take_arr);
             if (lane == 0)
             {
                 w.n[kNSeg] += got.to_segment; w.n[kNCol] += got.to_tail; w.n[kNLoad] -= got.to_segment + got.to_tail;
@@ -836,26 +844,33 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
 
 void QSB_EVT_LAUNCH_NAME(const TrackArgs& a, int grid, cudaStream_t s)
 {
+    // four instances: with / without the peer-exchange code, with / without the streamed-input queue.
     // QSB_FORCE_PEER_INSTANCE=1 (measurements only): run the instance that carries the peer-exchange code on a single GPU
     static const bool force_peer_instance = std::getenv("QSB_FORCE_PEER_INSTANCE") != nullptr;
-    if (a.peer_mode || force_peer_instance) track_warpq_kernel<QSB_VALIDATION, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
-    else             track_warpq_kernel<QSB_VALIDATION, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    const bool peer = a.peer_mode || force_peer_instance, stream = a.n_in != 0ull;
+    if (peer && stream) track_warpq_kernel<QSB_VALIDATION, 1, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    else if (peer)      track_warpq_kernel<QSB_VALIDATION, 1, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    else if (stream)    track_warpq_kernel<QSB_VALIDATION, 0, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
+    else                track_warpq_kernel<QSB_VALIDATION, 0, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
 }
 
 // registers per thread, resident blocks per SM, threads per block, shared-memory bytes per block, particle slots per block
 void QSB_EVT_ATTR_NAME(int* regs, int* max_blocks_per_sm, int* threads, int* smem_bytes, int* slots)
 {
-    cudaFuncSetAttribute(track_warpq_kernel<QSB_VALIDATION, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqShared));
-    cudaFuncSetAttribute(track_warpq_kernel<QSB_VALIDATION, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqShared));
-    cudaFuncAttributes attr;
-    int r = 0;
-    if (cudaFuncGetAttributes(&attr, track_warpq_kernel<QSB_VALIDATION, 0>) == cudaSuccess) r = attr.numRegs;
-    if (cudaFuncGetAttributes(&attr, track_warpq_kernel<QSB_VALIDATION, 1>) == cudaSuccess && attr.numRegs > r) r = attr.numRegs;
+    const void* kernels[4] = { (const void*)track_warpq_kernel<QSB_VALIDATION, 0, 0>, (const void*)track_warpq_kernel<QSB_VALIDATION, 0, 1>,
+                               (const void*)track_warpq_kernel<QSB_VALIDATION, 1, 0>, (const void*)track_warpq_kernel<QSB_VALIDATION, 1, 1> };
+    int r = 0, blocks = 1 << 30;
+    for (const void* k : kernels)
+    {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WqShared));
+        cudaFuncAttributes attr;
+        if (cudaFuncGetAttributes(&attr, k) == cudaSuccess && attr.numRegs > r) r = attr.numRegs;
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kWqThreads, sizeof(WqShared));
+        if (n < blocks) blocks = n;
+    }
     if (regs) *regs = r;
-    int n0 = 0, n1 = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n0, track_warpq_kernel<QSB_VALIDATION, 0>, kWqThreads, sizeof(WqShared));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, track_warpq_kernel<QSB_VALIDATION, 1>, kWqThreads, sizeof(WqShared));
-    if (max_blocks_per_sm) *max_blocks_per_sm = n0 < n1 ? n0 : n1;
+    if (max_blocks_per_sm) *max_blocks_per_sm = blocks;
     if (threads) *threads = kWqThreads;
     if (smem_bytes) *smem_bytes = (int)sizeof(WqShared);
     if (slots) *slots = kWqSlots;
