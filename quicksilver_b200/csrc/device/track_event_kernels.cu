@@ -226,53 +226,78 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
     unsigned long long in_seen = s.w[warp].in_seen;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStLoad; });
     WqLoaded out = { 0, 0, 0, 0, 0, 0 };
-    for (unsigned first = 0; first < total; first += 32u)
+
+    // ---- tickets for every empty slot of the warp, in ONE transaction: the queue counters are read together (one L2 round
+    // trip), the heads are advanced together (a second one) -- a LOAD used to pay a dependent global atomic per batch of 32,
+    // and three to five dependent accesses per batch once there were several queues.  Slot j of the list (batch j / 32, lane
+    // j % 32) that has no ticket gets the next one; rank = its position among the wanting slots in list order.
+    unsigned long long held[kWqK];
+    unsigned before[kWqK];                              // wanting slots in earlier batches + lower lanes of this batch
+    unsigned n_want = 0;
+#pragma unroll
+    for (int k = 0; k < kWqK; ++k)
+    {
+        const bool active = 32u * k + lane < total;
+        held[k] = active ? s.id[base + s.list[warp][32 * k + lane]] : 0ull;       // 0: not a candidate (a real ticket of value 0 is not kNoTicket either)
+        const unsigned m = __ballot_sync(kFullMask, active && held[k] == kNoTicket);
+        before[k] = n_want + __popc(m & ((1u << lane) - 1u));
+        n_want += __popc(m);
+    }
+    if (n_want)
+    {
+        unsigned k_a = 0, k_v = 0, k_in = 0;
+        unsigned long long c_tail = 0, c_head = 0, c_atail = 0, c_ahead = 0, c_hin = 0;
+        const bool input_maybe = kStream && n_in != 0ull && s.w[warp].input_left != 0u;
+        if (has_arrivals || input_maybe)
+        {
+            // lane 0: vault tail, 1: vault head, 2: arrival tail, 3: arrival head, 4: input head -- one load instruction
+            unsigned long long v = 0;
+            const unsigned long long* src = lane == 0 ? a.tail : lane == 1 ? &a.ctl->head : lane == 2 ? &peer_control(a, a.my_rank)->arr_tail
+                                          : lane == 3 ? &a.ctl->arr_head : &a.ctl->head_in;
+            if (lane < 2 || (has_arrivals && lane < 4) || (input_maybe && lane == 4)) v = ld_relaxed_u64(src);
+            c_tail = __shfl_sync(kFullMask, v, 0); c_head = __shfl_sync(kFullMask, v, 1);
+            if (kPeer) { c_atail = __shfl_sync(kFullMask, v, 2); c_ahead = __shfl_sync(kFullMask, v, 3); }
+            if (kStream) c_hin = __shfl_sync(kFullMask, v, 4);
+        }
+        const bool input_left = input_maybe && c_hin < n_in;
+        if (kStream && lane == 0 && !input_left) s.w[warp].input_left = 0u;
+        unsigned left = n_want;
+        if (has_arrivals && may_take_arr && c_atail > c_ahead)     // peer mode: particles other GPUs have deposited come first
+        { k_a = (unsigned)min((unsigned long long)left, c_atail - c_ahead); left -= k_a; }
+        if (input_left || has_arrivals)                            // vault tickets only for slots that exist
+        {
+            if (may_take_vault && c_tail > c_head) { k_v = (unsigned)min((unsigned long long)left, c_tail - c_head); left -= k_v; }
+            if (input_left && may_take_in) k_in = left;
+        }
+        else k_v = may_take_vault ? left : 0u;
+        // lane 0 advances the vault head, lane 1 the arrival head, lane 2 the input head -- one atomic instruction
+        unsigned long long tb = 0;
+        if (lane == 0 && k_v) tb = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
+        if (kPeer && lane == 1 && k_a) tb = atomicAdd(&a.ctl->arr_head, (unsigned long long)k_a);
+        if (kStream && lane == 2 && k_in) tb = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
+        const unsigned long long tb_v = __shfl_sync(kFullMask, tb, 0);
+        const unsigned long long tb_a = kPeer ? __shfl_sync(kFullMask, tb, 1) : 0ull;
+        const unsigned long long tb_in = kStream ? __shfl_sync(kFullMask, tb, 2) : 0ull;
+#pragma unroll
+        for (int k = 0; k < kWqK; ++k)
+        {
+            if (held[k] != kNoTicket) continue;
+            unsigned r = before[k];
+            if (r < k_a) held[k] = kArrivalTicket + tb_a + r;
+            else if ((r -= k_a) < k_v) held[k] = tb_v + r;
+            else if (kStream && r - k_v < k_in && tb_in + (r - k_v) < n_in) held[k] = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
+        }
+    }
+
+#pragma unroll 1
+    for (unsigned first = 0, k = 0; first < total; first += 32u, ++k)      // (not unrolled: one copy of the particle-load code)
     {
         const bool active = first + lane < total;
         const unsigned slot = base + (active ? s.list[warp][first + lane] : 0u);
-        unsigned long long ticket = active ? s.id[slot] : kNoTicket;
-        const bool want = active && ticket == kNoTicket;
-        const unsigned want_mask = __ballot_sync(kFullMask, want);
-        if (want_mask)
-        {
-            unsigned n_want = __popc(want_mask);
-            unsigned long long tb_v = 0, tb_in = 0, tb_a = 0;
-            unsigned k_v = 0, k_in = 0, k_a = 0;
-            const unsigned leader = __ffs(want_mask) - 1;
-            if (lane == leader)
-            {
-                if (has_arrivals && may_take_arr)         // peer mode: particles other GPUs have deposited come first
-                {
-                    const unsigned long long t = ld_relaxed_u64(&peer_control(a, a.my_rank)->arr_tail), h = ld_relaxed_u64(&a.ctl->arr_head);
-                    k_a = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
-                    if (k_a) { tb_a = atomicAdd(&a.ctl->arr_head, (unsigned long long)k_a); n_want -= k_a; }
-                }
-                const bool input_left = kStream && n_in != 0ull && s.w[warp].input_left && ld_relaxed_u64(&a.ctl->head_in) < n_in;
-                if (kStream && !input_left) s.w[warp].input_left = 0u;
-                if (input_left || has_arrivals)                    // vault tickets only for slots that exist
-                {
-                    if (may_take_vault && n_want)
-                    {
-                        const unsigned long long t = ld_relaxed_u64(a.tail), h = ld_relaxed_u64(&a.ctl->head);
-                        k_v = t > h ? (unsigned)min((unsigned long long)n_want, t - h) : 0u;
-                    }
-                    if (input_left && may_take_in) k_in = n_want - k_v;
-                }
-                else k_v = may_take_vault ? n_want : 0u;
-                if (k_v) tb_v = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
-                if (kStream && k_in) tb_in = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
-            }
-            tb_v = __shfl_sync(kFullMask, tb_v, leader); k_v = __shfl_sync(kFullMask, k_v, leader);
-            if (kStream) { tb_in = __shfl_sync(kFullMask, tb_in, leader); k_in = __shfl_sync(kFullMask, k_in, leader); }
-            if (has_arrivals) { tb_a = __shfl_sync(kFullMask, tb_a, leader); k_a = __shfl_sync(kFullMask, k_a, leader); }
-            if (want)
-            {
-                unsigned r = __popc(want_mask & ((1u << lane) - 1u));
-                if (r < k_a) ticket = kArrivalTicket + tb_a + r;
-                else if ((r -= k_a) < k_v) ticket = tb_v + r;
-                else if (kStream && r - k_v < k_in && tb_in + (r - k_v) < n_in) ticket = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
-            }
-        }
+        unsigned long long mine = held[0];
+#pragma unroll
+        for (int j = 1; j < kWqK; ++j) if (k == (unsigned)j) mine = held[j];
+        const unsigned long long ticket = active ? mine : kNoTicket;
         bool ready = false;
         unsigned long long vslot_of = 0;                // vault slot of a non-input ticket
         if (active && ticket != kNoTicket)
@@ -483,6 +508,16 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
         w0.in_seen = 0ull; w0.t_start = global_timer_ns(); w0.c_start = clock64();
     }
 
+#ifdef QSB_EXP_BLOAT
+    // experiment: ~2000 instructions that never run (a.dt is positive): does the sheer size of the kernel cost time?
+    if (a.dt < -1.0)
+    {
+        double v = a.dt;
+#pragma unroll
+        for (int k = 0; k < QSB_EXP_BLOAT; ++k) { v = qs_strict_log(v * v + 1.5) + (double)k; if (v > 3.0) __nanosleep(10); }
+        if (v == 0.123) atomicOr(&a.ctl->overflow, 16u);
+    }
+#endif
     for (;;)
     {
         __syncwarp();
@@ -566,7 +601,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
 
         if (type == kStLoad)            // the service phase: SEND, CENSUS, LOAD
         {
-            for (int left = n_snd; left > 0; left -= 32)
+            // sends ride along with a service phase once a few have gathered or when the warp has no full batch to run anyway:
+            // a deposit costs an NVLink round trip (~5 us, measured) whatever the number of particles in it
+            for (int left = (n_snd >= 8 || (n_seg < 32 && n_col < 32)) ? n_snd : 0; left > 0; left -= 32)
             {
                 const int n_act = wq_send<kPeer>(a, s, warp, lane);
                 if (lane == 0) { w.n[kNSnd] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
