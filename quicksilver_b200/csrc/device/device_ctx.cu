@@ -467,6 +467,9 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
                 }
             }
             im.compact = compact ? 1 : 0;
+            if (!compact && !c->opt.validation)
+                throw CudaFailure{ "image: the fast kernels need the uniform brick mesh of GlobalFccGrid (axis-aligned facet planes, < 65535 cells per axis, "
+                                   "<= 255 materials); this image is not one: use qsb_options.validation = 1" };
             im.cells = devUpload(recs.data(), nc, c->owned);
             // computed-neighbour path (DevImage::brick): the three strides are read off the first on-processor transit of each
             // axis and then checked on EVERY transit face of every cell; any exception (several domains per rank, a domain that

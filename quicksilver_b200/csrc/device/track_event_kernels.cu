@@ -123,6 +123,15 @@ constexpr int kWqK = (kWq + 31) / 32;               // ... per lane of bookkeepi
 constexpr int kWqWarps = QSB_WQ_WARPS;
 constexpr int kWqThreads = 32 * kWqWarps;
 constexpr int kWqSlots = kWq * kWqWarps;
+// the service events as functions of their own (1, default) or inlined into the kernel (0)
+#ifndef QSB_OPT_SERVICE_CALLS
+#define QSB_OPT_SERVICE_CALLS 1
+#endif
+#if QSB_OPT_SERVICE_CALLS
+#define QSB_WQ_SERVICE_FN __noinline__
+#else
+#define QSB_WQ_SERVICE_FN __forceinline__
+#endif
 #ifndef QSB_OPT_SERVICE_WATCHDOG
 #define QSB_OPT_SERVICE_WATCHDOG 1
 #endif
@@ -189,6 +198,103 @@ __device__ __forceinline__ unsigned wq_gather(WqShared& s, unsigned warp, unsign
 // COLLISION -- stays small enough for the instruction caches (the warp-state samples of the history kernel and of the first
 // event kernels showed 10-17 % of cycles waiting for instructions).
 
+// MC_Load_Particle (load_particle / load_particle_aos + reload_transform of track_physics.cuh: src/MC_Load_Particle.cc:11-29,
+// src/MC_Base_Particle.hh:287-331), vault record -> slot, a few fields at a time with compiler barriers in between: like the
+// census and the peer deposit this is a function whose register need, with the whole particle live, is paid for by spills in
+// the tracking batches.  Same arithmetic on the same values, field for field.
+template <class Store>
+__device__ __forceinline__ int finish_loaded_slot(const TrackArgs& a, Store& s, unsigned slot, bool raw, bool derive_direction)
+{
+    // what the transform computes: |velocity|, the direction cosine (from the record, or re-derived from the velocity:
+    // NaN marks "derive", the reference's MC_Particle(const MC_Base_Particle&) behaviour), the energy group
+    double speed = 0.0;
+    int group = 0;
+    if (!raw)
+    {
+        const double vx = s.alpha[slot], vy = s.beta[slot], vz = s.gamma[slot];       // parked there by the caller when the direction is to be derived
+        if (derive_direction)
+        {
+            speed = m_sqrt(vx * vx + vy * vy + vz * vz);
+            const double factor = m_div(1.0, speed);
+            s.alpha[slot] = factor * vx; s.beta[slot] = factor * vy; s.gamma[slot] = factor * vz;
+        }
+        group = energy_group(a, s.energy[slot]);
+    }
+    s.group[slot] = (unsigned short)group;
+    s.facet[slot] = (unsigned char)0;
+    if (!raw && derive_direction) s.speed[slot] = speed;
+    return raw ? kStateTail : kStateSegment;
+}
+
+template <class Store>
+__device__ __forceinline__ int load_slot_from_vault(const TrackArgs& a, Store& s, unsigned slot, unsigned long long i)
+{
+#define QSB_BARRIER asm volatile("" ::: "memory")
+    const VaultView& v = a.proc;
+    const int4 t = __ldcg(v.tags + i);
+    const bool raw = t.x == kRawChild;                  // a fission secondary as its parent wrote it: the collision tail finishes it
+    s.last_event[slot] = (unsigned char)(raw ? QSB_EV_COLLISION : t.x);
+    s.num_collisions[slot] = t.y; s.breed[slot] = t.z; s.species[slot] = t.w;
+    const int cell = __ldcg(v.cell + i);
+    s.cell[slot] = cell;
+    { const uint4 head = load_cell_head(a.im, cell); s.head01[slot] = make_uint2(head.x, head.y); s.events[slot] = head.z; } QSB_BARRIER;
+    s.x[slot] = __ldcg(v.x + i); s.y[slot] = __ldcg(v.y + i); s.z[slot] = __ldcg(v.z + i); QSB_BARRIER;
+    s.weight[slot] = __ldcg(v.weight + i); s.nmfp[slot] = __ldcg(v.nmfp + i); s.nseg[slot] = __ldcg(v.nseg + i); QSB_BARRIER;
+    s.seed[slot] = __ldcg(v.seed + i); s.id[slot] = __ldcg(v.id + i); s.energy[slot] = __ldcg(v.energy + i); QSB_BARRIER;
+    {
+        double ttc = __ldcg(v.ttc + i), age = __ldcg(v.age + i);
+        if (!raw) { if (ttc <= 0.0) ttc += a.dt; if (age < 0.0) age = 0.0; }
+        s.ttc[slot] = ttc; s.age[slot] = age;
+    }
+    QSB_BARRIER;
+    const double vx = __ldcg(v.vx + i), vy = __ldcg(v.vy + i), vz = __ldcg(v.vz + i);
+#if QSB_VALIDATION
+    s.vx[slot] = vx; s.vy[slot] = vy; s.vz[slot] = vz;
+#endif
+    const double dirx = __ldcg(v.dirx + i);
+    const bool derive = !raw && dirx != dirx;
+    if (derive) { s.alpha[slot] = vx; s.beta[slot] = vy; s.gamma[slot] = vz; }
+    else
+    {
+        s.alpha[slot] = dirx; s.beta[slot] = __ldcg(v.diry + i); s.gamma[slot] = __ldcg(v.dirz + i);
+        s.speed[slot] = raw ? 0.0 : m_sqrt(vx * vx + vy * vy + vz * vz);
+    }
+    QSB_BARRIER;
+    return finish_loaded_slot(a, s, slot, raw, derive);
+}
+
+// the same from record i of the streamed host vault (136-byte MC_Base_Particle records, load_particle_aos)
+template <class Store>
+__device__ __forceinline__ int load_slot_from_records(const TrackArgs& a, Store& s, unsigned slot, unsigned long long i)
+{
+    const double* __restrict__ r = reinterpret_cast<const double*>(a.in_aos + i);
+    const unsigned long long* __restrict__ u = reinterpret_cast<const unsigned long long*>(r);
+    const unsigned long long t0 = __ldcg(u + 14), t1 = __ldcg(u + 15), t2 = __ldcg(u + 16);
+    s.last_event[slot] = (unsigned char)(int)(unsigned)t0;
+    s.num_collisions[slot] = (int)(unsigned)(t0 >> 32); s.breed[slot] = (int)(unsigned)t1; s.species[slot] = (int)(unsigned)(t1 >> 32);
+    const int cell = __ldg(a.im.domain_cell_offset + (int)(unsigned)t2) + (int)(unsigned)(t2 >> 32);
+    s.cell[slot] = cell;
+    { const uint4 head = load_cell_head(a.im, cell); s.head01[slot] = make_uint2(head.x, head.y); s.events[slot] = head.z; } QSB_BARRIER;
+    s.x[slot] = __ldcg(r + 0); s.y[slot] = __ldcg(r + 1); s.z[slot] = __ldcg(r + 2); QSB_BARRIER;
+    s.weight[slot] = __ldcg(r + 7); s.nmfp[slot] = __ldcg(r + 10); s.nseg[slot] = __ldcg(r + 11); QSB_BARRIER;
+    s.seed[slot] = __ldcg(u + 12); s.id[slot] = __ldcg(u + 13); s.energy[slot] = __ldcg(r + 6); QSB_BARRIER;
+    {
+        double ttc = __ldcg(r + 8), age = __ldcg(r + 9);
+        if (ttc <= 0.0) ttc += a.dt;
+        if (age < 0.0) age = 0.0;
+        s.ttc[slot] = ttc; s.age[slot] = age;
+    }
+    QSB_BARRIER;
+    const double vx = __ldcg(r + 3), vy = __ldcg(r + 4), vz = __ldcg(r + 5);
+#if QSB_VALIDATION
+    s.vx[slot] = vx; s.vy[slot] = vy; s.vz[slot] = vz;
+#endif
+    s.alpha[slot] = vx; s.beta[slot] = vy; s.gamma[slot] = vz;
+    QSB_BARRIER;
+    return finish_loaded_slot(a, s, slot, false, true);
+#undef QSB_BARRIER
+}
+
 // LOAD: every slot of the warp without a particle; empty ones take a ticket (one global atomic per batch of 32), tickets
 // are redeemed once the vault slot they name has been written -- the history kernel's protocol (its service phase).
 //
@@ -217,7 +323,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 // neither (the tracking loop is instruction-cache bound: every instruction the refill path does not need is paid for in the
 // SEGMENT and COLLISION batches, measured)
 template <int kPeer, int kStream>
-__device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault,
+__device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane, bool may_take_in, bool may_take_vault,
                                          bool may_take_arr)
 {
     const bool has_arrivals = kPeer && a.arrival_cap != 0ull;
@@ -336,10 +442,8 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
         int state = kStateIdle;
         if (ready)
         {
-            Particle p;
-            if (kStream && ticket < n_in) { load_particle_aos(a, ticket, p); state = kStateSegment; }
-            else state = load_particle(a, vslot_of, p);
-            store_all(s, slot, p);
+            if (kStream && ticket < n_in) state = load_slot_from_records(a, s, slot, ticket);
+            else state = load_slot_from_vault(a, s, slot, vslot_of);
             s.state[slot] = (unsigned char)(state == kStateTail ? kStTail : kStSegment);
         }
         else if (active) s.id[slot] = ticket;
@@ -359,26 +463,94 @@ __device__ __noinline__ WqLoaded wq_load(const TrackArgs& a, WqShared& s, unsign
     return out;
 }
 
-// CENSUS: up to 32 histories that reached census; their records go to the census vault (or the streamed record buffer)
-__device__ __noinline__ int wq_census(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
+// CENSUS: up to 32 histories that reached census; their records go to the census vault (or the streamed record buffer).
+// Written slot -> global memory one field at a time (compiler barrier after each), like deposit_from_slot and for the same
+// reason: with the whole particle in registers this function's need, added to the kernel's at the call site, made the
+// 128-register build spill in the SEGMENT and COLLISION batches.
+template <class Store>
+__device__ __forceinline__ void census_from_slot(const TrackArgs& a, const Store& s, unsigned slot, unsigned long long i)
+{
+#define QSB_BARRIER asm volatile("" ::: "memory")
+    const int cell = s.cell[slot];
+    if (a.census_aos)                   // 136-byte record, src/MC_Base_Particle.hh:75-92 (store_census_aos)
+    {
+        double* r = reinterpret_cast<double*>(a.census_aos + i);
+        __stcg(r + 0, s.x[slot]); __stcg(r + 1, s.y[slot]); __stcg(r + 2, s.z[slot]); QSB_BARRIER;
+#if QSB_VALIDATION
+        __stcg(r + 3, s.vx[slot]); __stcg(r + 4, s.vy[slot]); __stcg(r + 5, s.vz[slot]); QSB_BARRIER;
+#else
+        { const double speed = s.speed[slot]; __stcg(r + 3, speed * s.alpha[slot]); __stcg(r + 4, speed * s.beta[slot]); __stcg(r + 5, speed * s.gamma[slot]); } QSB_BARRIER;
+#endif
+        __stcg(r + 6, s.energy[slot]); __stcg(r + 7, s.weight[slot]); __stcg(r + 8, s.ttc[slot]); QSB_BARRIER;
+        __stcg(r + 9, s.age[slot]); __stcg(r + 10, s.nmfp[slot]); __stcg(r + 11, s.nseg[slot]); QSB_BARRIER;
+        unsigned long long* u = reinterpret_cast<unsigned long long*>(r);
+        __stcg(u + 12, s.seed[slot]); __stcg(u + 13, s.id[slot]); QSB_BARRIER;
+        const int d = flat_to_domain(a.im, cell);
+        const int local = cell - __ldg(a.im.domain_cell_offset + d);
+        __stcg(u + 14, (unsigned long long)(unsigned)s.last_event[slot] | ((unsigned long long)(unsigned)s.num_collisions[slot] << 32));
+        __stcg(u + 15, (unsigned long long)(unsigned)s.breed[slot] | ((unsigned long long)(unsigned)s.species[slot] << 32));
+        __stcg(u + 16, (unsigned long long)(unsigned)d | ((unsigned long long)(unsigned)local << 32));
+    }
+    else                                // SoA census vault (store_particle, direction left to be re-derived: NaN)
+    {
+        const VaultView& v = a.census;
+        __stcg(v.x + i, s.x[slot]); __stcg(v.y + i, s.y[slot]); __stcg(v.z + i, s.z[slot]); QSB_BARRIER;
+#if QSB_VALIDATION
+        __stcg(v.vx + i, s.vx[slot]); __stcg(v.vy + i, s.vy[slot]); __stcg(v.vz + i, s.vz[slot]); QSB_BARRIER;
+#else
+        { const double speed = s.speed[slot]; __stcg(v.vx + i, speed * s.alpha[slot]); __stcg(v.vy + i, speed * s.beta[slot]); __stcg(v.vz + i, speed * s.gamma[slot]); } QSB_BARRIER;
+#endif
+        __stcg(v.energy + i, s.energy[slot]); __stcg(v.weight + i, s.weight[slot]); __stcg(v.ttc + i, s.ttc[slot]); QSB_BARRIER;
+        __stcg(v.age + i, s.age[slot]); __stcg(v.nmfp + i, s.nmfp[slot]); __stcg(v.nseg + i, s.nseg[slot]); QSB_BARRIER;
+        __stcg(v.seed + i, s.seed[slot]); __stcg(v.id + i, s.id[slot]); QSB_BARRIER;
+        __stcg(v.cell + i, cell);
+        __stcg(v.tags + i, make_int4((int)s.last_event[slot], s.num_collisions[slot], s.breed[slot], s.species[slot]));
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        __stcg(v.dirx + i, nan); __stcg(v.diry + i, nan); __stcg(v.dirz + i, nan);
+    }
+#undef QSB_BARRIER
+}
+
+__device__ QSB_WQ_SERVICE_FN int wq_census(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
 {
     const unsigned base = warp * kWq;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStCensus; });
-    const bool active = lane < total;
+    const bool active = lane < total;                   // the batch: lanes 0 .. count-1, list order
     const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
-    Particle p;
-    if (active) load_all(s, slot, p);
-    const unsigned mask = __ballot_sync(kFullMask, active);
+    const unsigned count = min(total, 32u);
     unsigned long long cbase = 0;
-    unsigned count = 0;
-    if (lane == 0)
+    if (lane == 0) cbase = atomicAdd(&a.ctl->census_count, (unsigned long long)count);
+    cbase = __shfl_sync(kFullMask, cbase, 0);
+    if (active)
     {
-        count = __popc(mask);
-        cbase = atomicAdd(&a.ctl->census_count, (unsigned long long)count);
+        if (cbase + lane >= a.census.capacity) atomicOr(&a.ctl->overflow, 2u);
+        else census_from_slot(a, s, slot, cbase + lane);
+        s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad;
     }
-    census_flush(a, p, active, lane, cbase, count, 0u, lane);
-    if (active) { s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad; }
-    return __popc(mask);
+    if (a.census_aos)
+    {
+        // streaming: count the batch's records into their chunk(s) with release semantics -- the records of the whole warp
+        // (ordered by the __syncwarp) are visible before the count -- and tell the host about every chunk that became
+        // complete, through mapped pinned memory; its D2H copy then runs while tracking continues (census_flush)
+        __syncwarp();
+        if (lane == 0)
+        {
+            const unsigned long long last = min(cbase + count, a.census.capacity);
+            unsigned long long at = cbase;
+            while (at < last)
+            {
+                const unsigned long long chunk = at >> a.census_chunk_shift;
+                const unsigned long long chunk_end = min((chunk + 1) << a.census_chunk_shift, last);
+                const unsigned cnt = (unsigned)(chunk_end - at);
+                unsigned old;
+                asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(a.census_chunk_done + chunk), "r"(cnt) : "memory");
+                if (old + cnt == (1u << a.census_chunk_shift))
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.host_chunk_flags + chunk), "r"(a.epoch) : "memory");
+                at = chunk_end;
+            }
+        }
+    }
+    return (int)count;
 }
 
 // SEND: up to 32 particles whose facet crossing leaves this rank's domain.  NCCL-rounds mode: packed into the per-peer slab
@@ -386,27 +558,62 @@ __device__ __noinline__ int wq_census(const TrackArgs& a, WqShared& s, unsigned 
 // NVLink; the remote counters are raised once per (batch, destination) instead of once per particle, in the order the
 // termination test relies on (peer's `sent` and `inflight` before the record is stored and the history retired here; peer's
 // `received` after its `inflight`), see send_advance in track_physics.cuh.
+// A particle's record, straight from its slot into slot i of a PEER's vault (what store_deposit does from registers): one
+// field at a time, with a compiler barrier after each, so that the function needs a handful of registers instead of the
+// whole particle.  That matters far from here: the register need of this rarely-run function is added to what the kernel
+// keeps live at its call site, and the allocator answered by spilling in the SEGMENT and COLLISION batches of the
+// peer-exchange instance (measured: +14 % at 168 registers, +36 % at 128).
+template <class Store>
+__device__ __forceinline__ void deposit_from_slot(const Store& s, unsigned slot, char* peer_base, unsigned long long cap, unsigned long long i,
+                                                  int cell, uint32_t vault_epoch)
+{
+    double* d = reinterpret_cast<double*>(peer_base + kVaultHeaderBytes);      // array k of vault_view starts at d + k * cap
+    unsigned long long x = deposit_salt(vault_epoch) ^ (unsigned long long)(unsigned)cell;
+#define QSB_DEPOSIT_F64(k_, value_) { const double v_ = (value_); __stcg(d + (unsigned long long)(k_) * cap + i, v_); x ^= bits(v_); asm volatile("" ::: "memory"); }
+    QSB_DEPOSIT_F64(0, s.x[slot]) QSB_DEPOSIT_F64(1, s.y[slot]) QSB_DEPOSIT_F64(2, s.z[slot])
+#if QSB_VALIDATION
+    QSB_DEPOSIT_F64(3, s.vx[slot]) QSB_DEPOSIT_F64(4, s.vy[slot]) QSB_DEPOSIT_F64(5, s.vz[slot])
+#else
+    QSB_DEPOSIT_F64(3, s.speed[slot] * s.alpha[slot]) QSB_DEPOSIT_F64(4, s.speed[slot] * s.beta[slot]) QSB_DEPOSIT_F64(5, s.speed[slot] * s.gamma[slot])
+#endif
+    QSB_DEPOSIT_F64(6, s.energy[slot]) QSB_DEPOSIT_F64(7, s.weight[slot]) QSB_DEPOSIT_F64(8, s.ttc[slot]) QSB_DEPOSIT_F64(9, s.age[slot])
+    QSB_DEPOSIT_F64(10, s.nmfp[slot]) QSB_DEPOSIT_F64(11, s.nseg[slot])
+    QSB_DEPOSIT_F64(12, s.alpha[slot]) QSB_DEPOSIT_F64(13, s.beta[slot]) QSB_DEPOSIT_F64(14, s.gamma[slot])
+#undef QSB_DEPOSIT_F64
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(d);
+    { const unsigned long long v = s.seed[slot]; __stcg(u + 15 * cap + i, v); x ^= v; }
+    { const unsigned long long v = s.id[slot];   __stcg(u + 16 * cap + i, v); x ^= v; }
+    asm volatile("" ::: "memory");
+    const int4 tags = make_int4((int)s.last_event[slot], s.num_collisions[slot], s.breed[slot], s.species[slot]);
+    x ^= (unsigned long long)(unsigned)tags.x | ((unsigned long long)(unsigned)tags.y << 32);
+    x ^= (unsigned long long)(unsigned)tags.z | ((unsigned long long)(unsigned)tags.w << 32);
+    __stcg(reinterpret_cast<int4*>(d + 18 * cap) + i, tags);
+    int* cells = reinterpret_cast<int*>(d + 20 * cap);
+    __stcg(cells + i, cell);
+    __stcg(u + 17 * cap + i, x);
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(reinterpret_cast<uint32_t*>(cells + cap) + i), "r"(vault_epoch | kArrivalBit) : "memory");
+}
+
 template <int kPeer>
-__device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
+__device__ QSB_WQ_SERVICE_FN int wq_send(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
 {
     const long long t_enter = clock64();
     const unsigned base = warp * kWq;
     const unsigned total = wq_gather(s, warp, lane, [](unsigned char st) { return st == kStSend; });
     const bool active = lane < total;
     const unsigned slot = base + (active ? s.list[warp][lane] : 0u);
-    Particle p;
-    if (active) load_all(s, slot, p);
     if (!(kPeer && a.peer_mode))
     {
+        Particle p;
         Counters unused = {};
-        if (active) facet_crossing_event(a, p, unused);     // TRANSIT_OFF: writes the exchange record into the per-peer slab
+        if (active) { load_all(s, slot, p); facet_crossing_event(a, p, unused); }     // TRANSIT_OFF: writes the exchange record into the per-peer slab
     }
     else if (kPeer)
     {
         const DevImage& im = a.im;
         int rank = -1;
         size_t k = 0;
-        if (active) { k = (size_t)p.cell * 6 + (p.facet >> 2); rank = __ldg(im.face_nbr_rank + k); }
+        if (active) { k = (size_t)s.cell[slot] * 6 + (s.facet[slot] >> 2); rank = __ldg(im.face_nbr_rank + k); }
         unsigned todo = __ballot_sync(kFullMask, active);
         while (todo)
         {
@@ -443,7 +650,7 @@ __device__ __noinline__ int wq_send(const TrackArgs& a, WqShared& s, unsigned wa
                     atomicAdd_system(&pc->inflight, 0ull - 1ull);
                 }
                 else
-                    store_deposit(vault_view(a.peer_base[dest], a.proc.capacity), vslot, p, peer_destination_cell(a, pc, k), s.launch[dest].vault_epoch);
+                    deposit_from_slot(s, slot, a.peer_base[dest], a.proc.capacity, vslot, peer_destination_cell(a, pc, k), s.launch[dest].vault_epoch);
             }
             __syncwarp();
             if (lane == head_lane)

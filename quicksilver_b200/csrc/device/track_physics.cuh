@@ -559,14 +559,12 @@ __device__ __forceinline__ int segment_outcome(const TrackArgs& a, Particle& p, 
         nf_facet = f2; d_facet = d2;
     }
 #else
-    if (!fast)          // a mesh that is not the uniform brick grid (never built by the host model), or a zero direction vector
+    if (!fast)          // a zero direction vector (the fast build is only ever launched on the uniform brick grid: qsb_create)
     {
-        int f2; double d2;
-        double qx = p.x, qy = p.y, qz = p.z;
-        nearest_facet_full(im.planes + (size_t)p.cell * 24, im.nodes + (size_t)p.cell * 42, &qx, &qy, &qz,
-                           p.alpha, p.beta, p.gamma, p.nseg, &f2, &d2);
-        p.x = qx; p.y = qy; p.z = qz;
-        nf_facet = f2; d_facet = d2;
+        // The reference's 24-facet search finds no facet for it either and ends in its error path; here the particle simply has
+        // no facet to cross, and the segment is counted so that qsb_track can report it.  (The full search is not part of the
+        // fast build: called from here, with the particle live, it alone set the kernel's register floor.)
+        nf_facet = 0; d_facet = kHugeDouble;
         atomicAdd(&a.ctl->slow_geometry, 1ull);
     }
 #endif
