@@ -198,6 +198,26 @@ __device__ __forceinline__ unsigned wq_gather(WqShared& s, unsigned warp, unsign
 // COLLISION -- stays small enough for the instruction caches (the warp-state samples of the history kernel and of the first
 // event kernels showed 10-17 % of cycles waiting for instructions).
 
+// A fission secondary, raw (write_raw_child of track_physics.cuh): the parent's record as its slot holds it at the collision --
+// the slot is only updated by the collision tail, after this -- with the child's stream and sampled outcome, slot -> vault a
+// few fields at a time (see deposit_from_slot for why).
+template <class Store>
+__device__ __noinline__ void raw_child_from_slot(const TrackArgs& a, const Store& s, unsigned slot, unsigned long long i, uint64_t child_seed,
+                                                 double energy_out, double angle_out)
+{
+    const VaultView& v = a.proc;
+    __stcg(v.x + i, s.x[slot]); __stcg(v.y + i, s.y[slot]); __stcg(v.z + i, s.z[slot]); asm volatile("" ::: "memory");
+#if QSB_VALIDATION
+    __stcg(v.vx + i, s.vx[slot]); __stcg(v.vy + i, s.vy[slot]); __stcg(v.vz + i, s.vz[slot]); asm volatile("" ::: "memory");
+#endif                          // fast build: the child's velocity is rebuilt by its collision tail before anything reads it
+    __stcg(v.energy + i, energy_out); __stcg(v.weight + i, s.weight[slot]); __stcg(v.ttc + i, s.ttc[slot]); asm volatile("" ::: "memory");
+    __stcg(v.age + i, s.age[slot]); __stcg(v.nmfp + i, angle_out); __stcg(v.nseg + i, s.nseg[slot]); asm volatile("" ::: "memory");
+    __stcg(v.seed + i, (unsigned long long)child_seed); __stcg(v.id + i, (unsigned long long)child_seed);
+    __stcg(v.cell + i, s.cell[slot]);
+    __stcg(v.tags + i, make_int4(kRawChild, s.num_collisions[slot], s.breed[slot], s.species[slot])); asm volatile("" ::: "memory");
+    __stcg(v.dirx + i, s.alpha[slot]); __stcg(v.diry + i, s.beta[slot]); __stcg(v.dirz + i, s.gamma[slot]);
+}
+
 // MC_Load_Particle (load_particle / load_particle_aos + reload_transform of track_physics.cuh: src/MC_Load_Particle.cc:11-29,
 // src/MC_Base_Particle.hh:287-331), vault record -> slot, a few fields at a time with compiler barriers in between: like the
 // census and the peer deposit this is a function whose register need, with the whole particle live, is paid for by spills in
@@ -1000,11 +1020,9 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
                     }
                     else
                     {
-                        Particle parent;
-                        load_all(s, slot, parent);
-                        write_raw_child(a, first, parent, qs_rng_spawn(&seed), energy1, angle1);
-                        if (n_child > 1u) write_raw_child(a, first + 1, parent, qs_rng_spawn(&seed), energy2, angle2);
-                        if (n_child > 2u) write_raw_child(a, first + 2, parent, qs_rng_spawn(&seed), energy3, angle3);
+                        raw_child_from_slot(a, s, slot, first, qs_rng_spawn(&seed), energy1, angle1);
+                        if (n_child > 1u) raw_child_from_slot(a, s, slot, first + 1, qs_rng_spawn(&seed), energy2, angle2);
+                        if (n_child > 2u) raw_child_from_slot(a, s, slot, first + 2, qs_rng_spawn(&seed), energy3, angle3);
                         s.pub_first[threadIdx.x] = first; s.pub_n[threadIdx.x] = n_child;       // published at the top of the next iteration
                     }
                 }
