@@ -336,7 +336,8 @@ int  qsb_peer_disconnect(qsb_ctx* ctx);
 /* timings of the last peer-mode qsb_track on this rank, measured on the device: [0] kernel start -> this GPU first had nothing
  * queued or running (ns), [1] kernel start -> global termination seen (ns), [2] SM cycles its warps spent depositing particles
  * on peers (summed over warps), [3] deposit passes, [4] wait for the peers' launch at kernel start (ns), [5] tickets used,
- * [6] particles deposited on peers, [7] reserved (0).  The tail of a cycle is [1] - [0]. */
+ * [6] particles deposited on peers, [7] kernel start -> a warp first found this GPU's own vault queue empty (ns; event kernel:
+ * what is tracked after that are arrivals and the chains of hops they start).  The tail of a cycle is [1] - [0]. */
 int  qsb_peer_diagnostics(qsb_ctx* ctx, uint64_t out[8]);
 const char* qsb_last_error(qsb_ctx* ctx);
 /* diagnostics of the current cycle: [0] segments that took the full 24-facet geometry path, [1] check-mode (geometry or reaction)

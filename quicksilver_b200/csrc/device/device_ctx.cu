@@ -1058,7 +1058,7 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
             c->h_peer->epoch = c->peer_epoch;
             QSB_CUDA(cudaMemcpyAsync(&d_peer->inflight, &c->h_peer->inflight, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
             QSB_CUDA(cudaMemcpyAsync(&d_peer->tail, &c->h_peer->tail, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-            QSB_CUDA(cudaMemsetAsync(&d_peer->first_idle_ns, 0, 5 * sizeof(unsigned long long), c->stream));          // this launch's diagnostics
+            QSB_CUDA(cudaMemsetAsync(&d_peer->first_idle_ns, 0, 6 * sizeof(unsigned long long), c->stream));          // this launch's diagnostics
             QSB_CUDA(cudaMemcpyAsync(&d_peer->n_in, &c->h_peer->n_in, 16, cudaMemcpyHostToDevice, c->stream));        // n_in + vault_epoch + epoch
         }
         if (c->streaming && !c->stream_input_issued)
@@ -1404,7 +1404,7 @@ int qsb_peer_diagnostics(qsb_ctx* c, uint64_t out[8])
         unsigned long long sent = 0;
         for (int r = 0; r < c->n_ranks; ++r) sent += c->h_ctl->send_count[r];
         out[0] = c->h_peer->first_idle_ns; out[1] = c->h_peer->done_ns; out[2] = c->h_peer->send_cycles; out[3] = c->h_peer->send_calls;
-        out[4] = c->h_peer->startup_wait_ns; out[5] = c->h_peer->tail; out[6] = sent; out[7] = 0;
+        out[4] = c->h_peer->startup_wait_ns; out[5] = c->h_peer->tail; out[6] = sent; out[7] = c->h_peer->bulk_done_ns;
         return (int)QSB_OK;
     });
 }

@@ -167,7 +167,8 @@ struct PeerControl
     unsigned long long send_cycles;     //   SM cycles warps spent inside send_advance, summed over warps; calls; start-up wait cycles (block 0)
     unsigned long long send_calls;
     unsigned long long startup_wait_ns;
-    unsigned int pad5[14];
+    unsigned long long bulk_done_ns;    //   kernel start -> a warp first found this GPU's own vault queue empty (what follows is arrivals and their chains)
+    unsigned int pad5[12];
     // written once by qsb_peer_export: where each of this rank's domains starts in its flat cell index space (a depositing
     // peer knows the destination as (rank-local domain, cell) and stores the flat cell, src/initMC.cc:256-259: a rank may own
     // several domains)

@@ -396,6 +396,11 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
             if (input_left && may_take_in) k_in = left;
         }
         else k_v = may_take_vault ? left : 0u;
+        if (kPeer && has_arrivals && lane == 0 && c_tail <= c_head)       // diagnostics: when did this GPU run out of its own work?
+        {
+            PeerControl* me = peer_control(a, a.my_rank);
+            if (*((volatile unsigned long long*)&me->bulk_done_ns) == 0ull) me->bulk_done_ns = global_timer_ns() - s.w[warp].t_start;
+        }
         // lane 0 advances the vault head, lane 1 the arrival head, lane 2 the input head -- one atomic instruction
         unsigned long long tb = 0;
         if (lane == 0 && k_v) tb = atomicAdd(&a.ctl->head, (unsigned long long)k_v);

@@ -172,7 +172,7 @@ class DeviceContext:
         """device-side timings of the last peer-mode launch (qsb_peer_diagnostics)"""
         out = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.qsb_peer_diagnostics(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
-        keys = ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "tickets", "deposited")
+        keys = ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "tickets", "deposited", "bulk_done_ns")
         return {k: int(v) for k, v in zip(keys, out)}
 
     def launch_count(self):

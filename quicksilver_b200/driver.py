@@ -464,7 +464,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
             sent_total += n_sent
             if world > 1 and getattr(sim, "exchange", "") == "peer":
                 d = ctx.peer_diagnostics()
-                for k in ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "deposited"):
+                for k in ("first_idle_ns", "done_ns", "send_cycles", "send_calls", "startup_wait_ns", "deposited", "bulk_done_ns"):
                     peer_diag[k] = peer_diag.get(k, 0) + d[k]
         step_kernel_s = sim.backend.device_ms * 1e-3 if world == 1 else tb - ta
         if timed:
@@ -619,7 +619,7 @@ def run_benchmark(args, warmup, rank, world, local_rank, workloads, grid_ladder,
         if peer_diag:
             mine.update(first_idle_ms=peer_diag["first_idle_ns"] * 1e-6 / k, done_ms=peer_diag["done_ns"] * 1e-6 / k,
                         tail_ms=(peer_diag["done_ns"] - peer_diag["first_idle_ns"]) * 1e-6 / k,
-                        startup_wait_ms=peer_diag["startup_wait_ns"] * 1e-6 / k,
+                        startup_wait_ms=peer_diag["startup_wait_ns"] * 1e-6 / k, own_queue_empty_ms=peer_diag.get("bulk_done_ns", 0) * 1e-6 / k,
                         send_mcycles_all_warps=peer_diag["send_cycles"] * 1e-6 / k, send_passes=peer_diag["send_calls"] // k)
         gathered = [None] * world
         dist.all_gather_object(gathered, mine)
