@@ -50,6 +50,26 @@ T* devUpload(const T* host, size_t n, std::vector<void*>& owned)
 // ---- small service kernels -------------------------------------------------------------------------
 
 // host AoS records (MC_Base_Particle layout) -> SoA slots [first, first+n) of the processing vault
+// boundary-first list (device_types.cuh, kPrioTicket): the vault slots below n whose cell is near another rank, in no
+// particular order (one atomic per warp); count -> ctl->prio_count
+__global__ void boundary_list_kernel(const int* __restrict__ cell, unsigned long long n, const uint8_t* __restrict__ cell_near,
+                                     uint32_t* __restrict__ list, unsigned long long* __restrict__ count)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long rounded = (n + 31ull) & ~31ull;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < rounded; i += stride)
+    {
+        const bool hit = i < n && cell_near[cell[i]] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0u) continue;
+        unsigned long long base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+}
+
 __global__ void aos_to_soa_kernel(const qsb_base_particle* __restrict__ in, unsigned long long n, VaultView v,
                                   unsigned long long first, const int* __restrict__ domain_cell_offset, uint32_t epoch)
 {
@@ -233,6 +253,7 @@ struct qsb_ctx
     size_t n_marks = 0;
     size_t n_chunks = 0;
     bool streaming = false, stream_input_issued = false;
+    uint32_t* d_prio_list = nullptr; size_t prio_list_cap = 0;   // boundary-first list (peer mode, event kernel)
     uint32_t arr_epoch = 0xffffffffu;           // cycle (vault epoch) the arrival region was last emptied for
     bool peer_multi_domain = false;             // some rank owns more than one domain (qsb_peer_connect)
     const qsb_base_particle* host_in = nullptr;
@@ -494,6 +515,32 @@ int qsb_create(int device, const qsb_image* image, double time_step, const qsb_o
                 std::vector<uint32_t> info(nc);
                 for (size_t cidx = 0; cidx < nc; ++cidx) info[cidx] = (recs[cidx].events & 0xffffffu) | ((uint32_t)recs[cidx].material << 24);
                 im.cell_info = devUpload(info.data(), nc, c->owned);
+                // cells within `depth` cells of a face that leads to another rank (DevImage::cell_near): breadth-first over the
+                // on-rank adjacency, starting from the cells that have such a face
+                im.cell_near = nullptr;
+                if (image->n_ranks > 1)
+                {
+                    int depth = 8;
+                    if (const char* e = std::getenv("QSB_BOUNDARY_DEPTH")) depth = std::max(0, std::atoi(e));
+                    std::vector<uint8_t> near(nc, 0);
+                    std::vector<uint32_t> frontier, next;
+                    for (size_t cidx = 0; cidx < nc; ++cidx)
+                        for (int face = 0; face < 6; ++face)
+                            if (image->face_event[cidx * 6 + face] == QSB_ADJ_TRANSIT_OFF) { near[cidx] = 1; frontier.push_back((uint32_t)cidx); break; }
+                    for (int d = 1; d < depth && !frontier.empty(); ++d)
+                    {
+                        next.clear();
+                        for (uint32_t cidx : frontier)
+                            for (int face = 0; face < 6; ++face)
+                                if (image->face_event[(size_t)cidx * 6 + face] == QSB_ADJ_TRANSIT_ON)
+                                {
+                                    const int32_t n = image->face_adj_cell[(size_t)cidx * 6 + face];
+                                    if (n >= 0 && (size_t)n < nc && !near[n]) { near[n] = 1; next.push_back((uint32_t)n); }
+                                }
+                        frontier.swap(next);
+                    }
+                    if (depth > 0) im.cell_near = devUpload(near.data(), nc, c->owned);
+                }
                 im.brick = (ok && std::getenv("QSB_NO_BRICK") == nullptr) ? 1 : 0;
                 for (int k = 0; k < 3; ++k) im.brick_stride[k] = stride[k];
             }
@@ -1003,13 +1050,34 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         a.check_mode = ((c->opt.tracking_mode & 2) ? 1 : 0) | ((c->opt.tracking_mode & 4) ? 2 : 0);
         a.in_aos = c->d_in_aos; a.n_in = c->n_in_aos;
         a.inflight = &c->d_ctl->inflight; a.tail = &c->d_ctl->tail;
-        a.peer_mode = 0; a.peer_multi_domain = 0; a.arrival_first = 0; a.arrival_cap = 0; a.my_rank = c->my_rank; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
+        a.peer_mode = 0; a.peer_multi_domain = 0; a.arrival_first = 0; a.arrival_cap = 0; a.prio_list = nullptr; a.prio_slots = 0; a.my_rank = c->my_rank;
+        uint32_t n_launch_pre = 0; a.peer_epoch = 0; a.watchdog_ns = c->watchdog_ns;
         for (int r = 0; r < kMaxPeers; ++r) a.peer_base[r] = c->peer_base[r];
         if (c->peer_on)
         {
             if (c->proc != 0) { c->error = "peer exchange: the exported processing vault is vault 0 (keep_census is not supported with it)"; return (int)QSB_ERR_STATE; }
             a.peer_mode = 1;
             a.peer_multi_domain = c->peer_multi_domain ? 1 : 0;
+#if QSB_OPT_BOUNDARY_FIRST
+            // boundary first: list the slots of the cycle's initial population whose history may reach another GPU (first launch of
+            // a cycle over a host-put / device-made population; not when the input is streamed or a launch continues a cycle)
+            if (c->event_mode && c->im.cell_near && c->consumed == 0 && c->n_in_aos == 0 && c->ready_prefix > 0 &&
+                c->ready_prefix < (1ull << 32) && std::getenv("QSB_NO_BOUNDARY_FIRST") == nullptr)
+            {
+                if (c->ready_prefix > c->prio_list_cap)
+                {
+                    c->prio_list_cap = (size_t)(c->ready_prefix + c->ready_prefix / 4 + 1024);
+                    c->d_prio_list = devAlloc<uint32_t>(c->prio_list_cap, c->owned);      // the previous, smaller one stays owned until destroy
+                }
+                QSB_CUDA(cudaMemsetAsync(&c->d_ctl->prio_head, 0, sizeof(unsigned long long), c->stream));
+                QSB_CUDA(cudaMemsetAsync(&c->d_ctl->prio_count, 0, sizeof(unsigned long long), c->stream));
+                const int grid = (int)std::min<unsigned long long>((c->ready_prefix + 255) / 256, (unsigned long long)c->sm_count * 16);
+                boundary_list_kernel<<<grid, 256, 0, c->stream>>>(a.proc.cell, c->ready_prefix, c->im.cell_near, c->d_prio_list, &c->d_ctl->prio_count);
+                QSB_CUDA(cudaGetLastError());
+                ++n_launch_pre; c->launches++;
+                a.prio_list = c->d_prio_list; a.prio_slots = c->ready_prefix;
+            }
+#endif
 #if QSB_OPT_ARRIVAL_QUEUE
             if (c->event_mode)
             {
@@ -1025,7 +1093,7 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
         }
         a.census_aos = c->streaming ? c->d_census_aos : nullptr;
         a.census_chunk_done = c->d_chunk_done; a.host_chunk_flags = c->d_chunk_flags; a.census_chunk_shift = kCensusChunkShift;
-        uint32_t n_launch = 0;
+        uint32_t n_launch = n_launch_pre;
         // tickets handed out past the tail by the previous call were never redeemed: restart at the consumed mark
         c->h_ctl->head = c->consumed;
         if (c->event_mode)

@@ -64,6 +64,9 @@ struct DevImage
     int brick;                      // 1: the computed-neighbour path is valid for this image
     int brick_stride[3];            // sx, sy, sz
     const uint32_t* cell_info;      // [n_cells] events (6 x 4 bits) | material << 24
+    // several ranks: 1 for cells within a few cells of a face that leads to another rank (breadth-first over the on-rank
+    // adjacency from the cells that have such a face); nullptr on a single rank.  See TrackArgs::prio_list.
+    const uint8_t* cell_near;
     // compact reaction table: when every material is periodic (one reaction table shared by its isotopes) only the first
     // isotope's rows are ever read: [n_materials][n_groups][compact_react] instead of rows of max_react doubles
     const double*  xs_compact;      // nullptr: not available
@@ -112,6 +115,10 @@ struct DevControl
     unsigned long long pad5[31];        // serves the vault slots only (tickets >= n_in), so secondaries do not queue behind the whole input
     unsigned long long arr_head;        // event kernel, peer mode: next unclaimed slot of the arrival region (its tail: PeerControl::arr_tail)
     unsigned long long pad6[31];
+    unsigned long long prio_head;       // event kernel, peer mode: next unclaimed entry of the boundary-first list (TrackArgs::prio_list)
+    unsigned long long pad7[31];
+    unsigned long long prio_count;      // entries in that list (written by boundary_list_kernel before the tracking launch)
+    unsigned long long pad8[31];
     unsigned long long slow_geometry;   // segments that took the full 24-facet path
     unsigned long long geometry_mismatch; // check mode: fast and full path disagreed (must stay 0)
     unsigned long long balance[QSB_BAL_COUNT];
@@ -142,6 +149,18 @@ constexpr int kMaxPeers = 8;
 #define QSB_OPT_ARRIVAL_QUEUE 1
 #endif
 constexpr unsigned long long kArrivalTicket = 1ull << 62;
+// Event kernel, peer mode: BOUNDARY FIRST.  A particle that crosses to another GPU starts a chain of hops (it may cross back
+// and forth: 11 exchange rounds in the NCCL mode of Coral2_P1), each hop a whole history segment chain on the other GPU; a
+// chain started at the end of the cycle is tracked on nearly empty GPUs, one hop after the other, and every rank waits for
+// it (measured on 2 GPUs: the kernel ran 2.3 ms beyond the 12.1 ms of its own work).  So the histories that can reach
+// another rank -- those starting within a few cells of an off-rank face, DevImage::cell_near -- are tracked FIRST: a small
+// kernel lists their vault slots (boundary_list_kernel), LOAD serves that list before the vault queue, and the vault queue
+// skips the slots the list holds (same predicate, so no slot is tracked twice and none is lost).  A list ticket is its index
+// + kPrioTicket.
+#ifndef QSB_OPT_BOUNDARY_FIRST
+#define QSB_OPT_BOUNDARY_FIRST 1
+#endif
+constexpr unsigned long long kPrioTicket = 1ull << 61;
 constexpr int kMaxDomainsPerRank = 64;
 struct PeerControl
 {
@@ -230,6 +249,8 @@ struct TrackArgs
     int peer_mode, my_rank;
     int peer_multi_domain;              // some rank owns more than one domain: a deposit adds the destination domain's offset (read from the peer)
     unsigned long long arrival_first, arrival_cap;  // the arrival region [arrival_first, arrival_first + arrival_cap) of every rank's vault (0: none)
+    const uint32_t* prio_list;          // boundary-first list: vault slots (< prio_slots) whose cell is near another rank; nullptr: none
+    unsigned long long prio_slots;      // the list was built over vault slots [0, prio_slots): the vault queue skips listed slots below it
     uint32_t peer_epoch;
     char* peer_base[kMaxPeers];
     unsigned long long watchdog_ns;     // give up (abort everywhere) when a launch has not terminated after this long

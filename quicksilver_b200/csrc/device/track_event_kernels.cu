@@ -369,27 +369,33 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
         before[k] = n_want + __popc(m & ((1u << lane) - 1u));
         n_want += __popc(m);
     }
+    const bool has_prio = kPeer && QSB_OPT_BOUNDARY_FIRST && a.prio_list != nullptr;
+    unsigned long long c_ptail = 0;
     if (n_want)
     {
-        unsigned k_a = 0, k_v = 0, k_in = 0;
-        unsigned long long c_tail = 0, c_head = 0, c_atail = 0, c_ahead = 0, c_hin = 0;
+        unsigned k_a = 0, k_v = 0, k_in = 0, k_p = 0;
+        unsigned long long c_tail = 0, c_head = 0, c_atail = 0, c_ahead = 0, c_hin = 0, c_phead = 0;
         const bool input_maybe = kStream && n_in != 0ull && s.w[warp].input_left != 0u;
         if (has_arrivals || input_maybe)
         {
-            // lane 0: vault tail, 1: vault head, 2: arrival tail, 3: arrival head, 4: input head -- one load instruction
+            // lane 0: vault tail, 1: vault head, 2: arrival tail, 3: arrival head, 4: input head, 5 / 6: boundary-first list head /
+            // length -- one load instruction
             unsigned long long v = 0;
             const unsigned long long* src = lane == 0 ? a.tail : lane == 1 ? &a.ctl->head : lane == 2 ? &peer_control(a, a.my_rank)->arr_tail
-                                          : lane == 3 ? &a.ctl->arr_head : &a.ctl->head_in;
-            if (lane < 2 || (has_arrivals && lane < 4) || (input_maybe && lane == 4)) v = ld_relaxed_u64(src);
+                                          : lane == 3 ? &a.ctl->arr_head : lane == 4 ? &a.ctl->head_in : lane == 5 ? &a.ctl->prio_head : &a.ctl->prio_count;
+            if (lane < 2 || (has_arrivals && lane < 4) || (input_maybe && lane == 4) || (has_prio && (lane == 5 || lane == 6))) v = ld_relaxed_u64(src);
             c_tail = __shfl_sync(kFullMask, v, 0); c_head = __shfl_sync(kFullMask, v, 1);
             if (kPeer) { c_atail = __shfl_sync(kFullMask, v, 2); c_ahead = __shfl_sync(kFullMask, v, 3); }
             if (kStream) c_hin = __shfl_sync(kFullMask, v, 4);
+            if (kPeer) { c_phead = __shfl_sync(kFullMask, v, 5); c_ptail = __shfl_sync(kFullMask, v, 6); }
         }
         const bool input_left = input_maybe && c_hin < n_in;
         if (kStream && lane == 0 && !input_left) s.w[warp].input_left = 0u;
         unsigned left = n_want;
         if (has_arrivals && may_take_arr && c_atail > c_ahead)     // peer mode: particles other GPUs have deposited come first
         { k_a = (unsigned)min((unsigned long long)left, c_atail - c_ahead); left -= k_a; }
+        if (has_prio && c_ptail > c_phead)                         // then the histories that may reach another GPU
+        { k_p = (unsigned)min((unsigned long long)left, c_ptail - c_phead); left -= k_p; }
         if (input_left || has_arrivals)                            // vault tickets only for slots that exist
         {
             if (may_take_vault && c_tail > c_head) { k_v = (unsigned)min((unsigned long long)left, c_tail - c_head); left -= k_v; }
@@ -406,17 +412,24 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
         if (lane == 0 && k_v) tb = atomicAdd(&a.ctl->head, (unsigned long long)k_v);
         if (kPeer && lane == 1 && k_a) tb = atomicAdd(&a.ctl->arr_head, (unsigned long long)k_a);
         if (kStream && lane == 2 && k_in) tb = atomicAdd(&a.ctl->head_in, (unsigned long long)k_in);
+        if (kPeer && lane == 3 && k_p) tb = atomicAdd(&a.ctl->prio_head, (unsigned long long)k_p);
         const unsigned long long tb_v = __shfl_sync(kFullMask, tb, 0);
         const unsigned long long tb_a = kPeer ? __shfl_sync(kFullMask, tb, 1) : 0ull;
         const unsigned long long tb_in = kStream ? __shfl_sync(kFullMask, tb, 2) : 0ull;
+        const unsigned long long tb_p = kPeer ? __shfl_sync(kFullMask, tb, 3) : 0ull;
+        out.unserved = (int)(n_want - k_a - k_p - k_v - k_in);
 #pragma unroll
         for (int k = 0; k < kWqK; ++k)
         {
             if (held[k] != kNoTicket) continue;
             unsigned r = before[k];
-            if (r < k_a) held[k] = kArrivalTicket + tb_a + r;
-            else if ((r -= k_a) < k_v) held[k] = tb_v + r;
-            else if (kStream && r - k_v < k_in && tb_in + (r - k_v) < n_in) held[k] = tb_in + (r - k_v);      // past the input's end: no ticket, next time a vault one
+            if (r < k_a) { held[k] = kArrivalTicket + tb_a + r; continue; }
+            r -= k_a;
+            if (r < k_p) { held[k] = kPrioTicket + tb_p + r; continue; }
+            r -= k_p;
+            if (r < k_v) { held[k] = tb_v + r; continue; }
+            r -= k_v;
+            if (kStream && r < k_in && tb_in + r < n_in) held[k] = tb_in + r;      // past the input's end: no ticket, next time a vault one
         }
     }
 
@@ -428,12 +441,20 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
         unsigned long long mine = held[0];
 #pragma unroll
         for (int j = 1; j < kWqK; ++j) if (k == (unsigned)j) mine = held[j];
-        const unsigned long long ticket = active ? mine : kNoTicket;
+        unsigned long long ticket = active ? mine : kNoTicket;
         bool ready = false;
         unsigned long long vslot_of = 0;                // vault slot of a non-input ticket
         if (active && ticket != kNoTicket)
         {
-            if (kPeer && ticket >= kArrivalTicket)
+            if (kPeer && ticket >= kPrioTicket && ticket < kArrivalTicket)
+            {
+                // an entry of the boundary-first list: a slot of the initial population, ready by construction (an index past the
+                // list's end can only come from two warps racing for its last entries: no ticket)
+                const unsigned long long t = ticket - kPrioTicket;
+                if (t < c_ptail) { vslot_of = __ldg(a.prio_list + t); ready = true; }
+                else ticket = kNoTicket;
+            }
+            else if (kPeer && ticket >= kArrivalTicket)
             {
                 const unsigned long long t = ticket - kArrivalTicket;
                 if (t < a.arrival_cap)
@@ -455,6 +476,8 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
                 const unsigned long long vslot = ticket - n_in;
                 vslot_of = vslot;
                 ready = vslot < a.ready_prefix;
+                if (has_prio && vslot < a.prio_slots && __ldg(a.im.cell_near + __ldcg(a.proc.cell + vslot)) != 0)
+                { ready = false; ticket = kNoTicket; }     // tracked through the boundary-first list: not this queue's
                 if (!ready)
                 {
                     uint32_t flag;
@@ -477,7 +500,6 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
         if (kStream) out.waiting_in += __popc(__ballot_sync(kFullMask, active && !ready && ticket < n_in));
         out.waiting_vault += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= n_in && ticket < kArrivalTicket));
         if (has_arrivals) out.waiting_arr += __popc(__ballot_sync(kFullMask, active && !ready && ticket >= kArrivalTicket && ticket != kNoTicket));
-        out.unserved += __popc(__ballot_sync(kFullMask, active && ticket == kNoTicket));
     }
     if (kStream)            // keep the highest DMA front any lane has seen
     {
@@ -492,12 +514,12 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
 // Written slot -> global memory one field at a time (compiler barrier after each), like deposit_from_slot and for the same
 // reason: with the whole particle in registers this function's need, added to the kernel's at the call site, made the
 // 128-register build spill in the SEGMENT and COLLISION batches.
-template <class Store>
+template <int kStream, class Store>
 __device__ __forceinline__ void census_from_slot(const TrackArgs& a, const Store& s, unsigned slot, unsigned long long i)
 {
 #define QSB_BARRIER asm volatile("" ::: "memory")
     const int cell = s.cell[slot];
-    if (a.census_aos)                   // 136-byte record, src/MC_Base_Particle.hh:75-92 (store_census_aos)
+    if (kStream && a.census_aos)        // 136-byte record, src/MC_Base_Particle.hh:75-92 (store_census_aos)
     {
         double* r = reinterpret_cast<double*>(a.census_aos + i);
         __stcg(r + 0, s.x[slot]); __stcg(r + 1, s.y[slot]); __stcg(r + 2, s.z[slot]); QSB_BARRIER;
@@ -536,6 +558,8 @@ __device__ __forceinline__ void census_from_slot(const TrackArgs& a, const Store
 #undef QSB_BARRIER
 }
 
+// kStream: the instance that can stream its census to the host as records (the launcher picks it whenever a.census_aos is set)
+template <int kStream>
 __device__ QSB_WQ_SERVICE_FN int wq_census(const TrackArgs& a, WqShared& s, unsigned warp, unsigned lane)
 {
     const unsigned base = warp * kWq;
@@ -549,10 +573,10 @@ __device__ QSB_WQ_SERVICE_FN int wq_census(const TrackArgs& a, WqShared& s, unsi
     if (active)
     {
         if (cbase + lane >= a.census.capacity) atomicOr(&a.ctl->overflow, 2u);
-        else census_from_slot(a, s, slot, cbase + lane);
+        else census_from_slot<kStream>(a, s, slot, cbase + lane);
         s.id[slot] = kNoTicket; s.state[slot] = (unsigned char)kStLoad;
     }
-    if (a.census_aos)
+    if (kStream && a.census_aos)
     {
         // streaming: count the batch's records into their chunk(s) with release semantics -- the records of the whole warp
         // (ordered by the __syncwarp) are visible before the count -- and tell the host about every chunk that became
@@ -589,34 +613,38 @@ __device__ QSB_WQ_SERVICE_FN int wq_census(const TrackArgs& a, WqShared& s, unsi
 // keeps live at its call site, and the allocator answered by spilling in the SEGMENT and COLLISION batches of the
 // peer-exchange instance (measured: +14 % at 168 registers, +36 % at 128).
 template <class Store>
-__device__ __forceinline__ void deposit_from_slot(const Store& s, unsigned slot, char* peer_base, unsigned long long cap, unsigned long long i,
-                                                  int cell, uint32_t vault_epoch)
+__device__ __noinline__ void deposit_from_slot(const Store& s, unsigned slot, char* peer_base, unsigned long long cap, unsigned long long i,
+                                               int cell, uint32_t vault_epoch)
 {
-    double* d = reinterpret_cast<double*>(peer_base + kVaultHeaderBytes);      // array k of vault_view starts at d + k * cap
+    // array k of vault_view starts at d + k * cap; a RUNNING pointer walks from array to array (twenty precomputed addresses
+    // would be forty registers, and the allocator would take them from the tracking batches)
+    double* d = reinterpret_cast<double*>(peer_base + kVaultHeaderBytes);
+    volatile unsigned long long step = cap;             // opaque to the optimiser: keeps the address arithmetic sequential
+    double* ptr = d + i;
     unsigned long long x = deposit_salt(vault_epoch) ^ (unsigned long long)(unsigned)cell;
-#define QSB_DEPOSIT_F64(k_, value_) { const double v_ = (value_); __stcg(d + (unsigned long long)(k_) * cap + i, v_); x ^= bits(v_); asm volatile("" ::: "memory"); }
-    QSB_DEPOSIT_F64(0, s.x[slot]) QSB_DEPOSIT_F64(1, s.y[slot]) QSB_DEPOSIT_F64(2, s.z[slot])
+#define QSB_DEPOSIT_F64(value_) { const double v_ = (value_); __stcg(ptr, v_); x ^= bits(v_); ptr += step; asm volatile("" ::: "memory"); }
+    QSB_DEPOSIT_F64(s.x[slot]) QSB_DEPOSIT_F64(s.y[slot]) QSB_DEPOSIT_F64(s.z[slot])
 #if QSB_VALIDATION
-    QSB_DEPOSIT_F64(3, s.vx[slot]) QSB_DEPOSIT_F64(4, s.vy[slot]) QSB_DEPOSIT_F64(5, s.vz[slot])
+    QSB_DEPOSIT_F64(s.vx[slot]) QSB_DEPOSIT_F64(s.vy[slot]) QSB_DEPOSIT_F64(s.vz[slot])
 #else
-    QSB_DEPOSIT_F64(3, s.speed[slot] * s.alpha[slot]) QSB_DEPOSIT_F64(4, s.speed[slot] * s.beta[slot]) QSB_DEPOSIT_F64(5, s.speed[slot] * s.gamma[slot])
+    QSB_DEPOSIT_F64(s.speed[slot] * s.alpha[slot]) QSB_DEPOSIT_F64(s.speed[slot] * s.beta[slot]) QSB_DEPOSIT_F64(s.speed[slot] * s.gamma[slot])
 #endif
-    QSB_DEPOSIT_F64(6, s.energy[slot]) QSB_DEPOSIT_F64(7, s.weight[slot]) QSB_DEPOSIT_F64(8, s.ttc[slot]) QSB_DEPOSIT_F64(9, s.age[slot])
-    QSB_DEPOSIT_F64(10, s.nmfp[slot]) QSB_DEPOSIT_F64(11, s.nseg[slot])
-    QSB_DEPOSIT_F64(12, s.alpha[slot]) QSB_DEPOSIT_F64(13, s.beta[slot]) QSB_DEPOSIT_F64(14, s.gamma[slot])
+    QSB_DEPOSIT_F64(s.energy[slot]) QSB_DEPOSIT_F64(s.weight[slot]) QSB_DEPOSIT_F64(s.ttc[slot]) QSB_DEPOSIT_F64(s.age[slot])
+    QSB_DEPOSIT_F64(s.nmfp[slot]) QSB_DEPOSIT_F64(s.nseg[slot])
+    QSB_DEPOSIT_F64(s.alpha[slot]) QSB_DEPOSIT_F64(s.beta[slot]) QSB_DEPOSIT_F64(s.gamma[slot])
 #undef QSB_DEPOSIT_F64
-    unsigned long long* u = reinterpret_cast<unsigned long long*>(d);
-    { const unsigned long long v = s.seed[slot]; __stcg(u + 15 * cap + i, v); x ^= v; }
-    { const unsigned long long v = s.id[slot];   __stcg(u + 16 * cap + i, v); x ^= v; }
+    unsigned long long* u = reinterpret_cast<unsigned long long*>(ptr);                 // array 15: seed
+    { const unsigned long long v = s.seed[slot]; __stcg(u, v); x ^= v; u += step; }    // 16: id
+    { const unsigned long long v = s.id[slot];   __stcg(u, v); x ^= v; u += step; }    // 17: check (stored last)
     asm volatile("" ::: "memory");
     const int4 tags = make_int4((int)s.last_event[slot], s.num_collisions[slot], s.breed[slot], s.species[slot]);
     x ^= (unsigned long long)(unsigned)tags.x | ((unsigned long long)(unsigned)tags.y << 32);
     x ^= (unsigned long long)(unsigned)tags.z | ((unsigned long long)(unsigned)tags.w << 32);
-    __stcg(reinterpret_cast<int4*>(d + 18 * cap) + i, tags);
-    int* cells = reinterpret_cast<int*>(d + 20 * cap);
+    __stcg(reinterpret_cast<int4*>(d + 18 * step) + i, tags);
+    int* cells = reinterpret_cast<int*>(d + 20 * step);
     __stcg(cells + i, cell);
-    __stcg(u + 17 * cap + i, x);
-    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(reinterpret_cast<uint32_t*>(cells + cap) + i), "r"(vault_epoch | kArrivalBit) : "memory");
+    __stcg(u, x);
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(reinterpret_cast<uint32_t*>(cells + step) + i), "r"(vault_epoch | kArrivalBit) : "memory");
 }
 
 template <int kPeer>
@@ -842,7 +870,7 @@ __global__ void __launch_bounds__(kWqThreads, QSB_WQ_MIN_BLOCKS) track_warpq_ker
             }
             for (int left = do_census ? n_cen : 0; left > 0; left -= 32)
             {
-                const int n_act = wq_census(a, s, warp, lane);
+                const int n_act = wq_census<kStream>(a, s, warp, lane);
                 if (lane == 0) { w.n[kNCen] -= n_act; w.n[kNLoad] += n_act; w.retired += (unsigned)n_act; }
             }
             if (!do_load) continue;
@@ -1114,7 +1142,7 @@ void QSB_EVT_LAUNCH_NAME(const TrackArgs& a, int grid, cudaStream_t s)
     // four instances: with / without the peer-exchange code, with / without the streamed-input queue.
     // QSB_FORCE_PEER_INSTANCE=1 (measurements only): run the instance that carries the peer-exchange code on a single GPU
     static const bool force_peer_instance = std::getenv("QSB_FORCE_PEER_INSTANCE") != nullptr;
-    const bool peer = a.peer_mode || force_peer_instance, stream = a.n_in != 0ull;
+    const bool peer = a.peer_mode || force_peer_instance, stream = a.n_in != 0ull || a.census_aos != nullptr;
     if (peer && stream) track_warpq_kernel<QSB_VALIDATION, 1, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
     else if (peer)      track_warpq_kernel<QSB_VALIDATION, 1, 0><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
     else if (stream)    track_warpq_kernel<QSB_VALIDATION, 0, 1><<<grid, kWqThreads, sizeof(WqShared), s>>>(a);
