@@ -401,7 +401,7 @@ def main():
     achieved = w["b_seg"] * seg_rank0 / ks_rank0 / 1e9 if ks_rank0 > 0 else 0.0
     dev_ms = result["tracking_ms_per_step_rank0"]["cuda_events_on_kernel_stream"]
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "peak_source": peak_src, "kernel": "track_kernel", "kernel_hash": kernel_hash, "evidence": evidence_note,
+            "traffic": traffic, "peak_source": peak_src, "kernel": "track_warpq_kernel (event-based; QSB_TRACKING=history: track_kernel)", "kernel_hash": kernel_hash, "evidence": evidence_note,
             # what the kernel really moves: ncu DRAM bytes of one full-size launch of THIS kernel / this run's launch time
             "dram_achieved": (traffic / (1e-3 * dev_ms) / 1e9) if traffic and world == 1 and dev_ms > 0 else None,
             "algorithmic_bytes_per_segment": w["b_seg"],

@@ -478,7 +478,7 @@ __device__ QSB_WQ_SERVICE_FN WqLoaded wq_load(const TrackArgs& a, WqShared& s, u
                 ready = vslot < a.ready_prefix;
                 if (has_prio && vslot < a.prio_slots && __ldg(a.im.cell_near + __ldcg(a.proc.cell + vslot)) != 0)
                 { ready = false; ticket = kNoTicket; }     // tracked through the boundary-first list: not this queue's
-                if (!ready)
+                else if (!ready)
                 {
                     uint32_t flag;
                     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(flag) : "l"(a.proc.ready + vslot) : "memory");
