@@ -15,6 +15,7 @@ from quicksilver_b200._capi import BAL, BAL_COUNT, EXCHANGE_DTYPE, PARTICLE_DTYP
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_QS = os.path.join(ORACLE_DIR, "_ref", "qs")
 REF_DUMP = os.path.join(ORACLE_DIR, "_ref", "qs_dump")
+REF_DUMP_STRICT = os.path.join(ORACLE_DIR, "_ref", "qs_dump_strict")     # the reference with log / sin / cos mapped to qs_strict_math.h
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -41,9 +42,9 @@ def particles_from_bytes(arr):
     return np.ascontiguousarray(arr).view(PARTICLE_DTYPE).reshape(-1)
 
 
-def run_reference_dump(argv, out_dir, particle_cycles=1, threads=4):
+def run_reference_dump(argv, out_dir, particle_cycles=1, threads=4, exe=None):
     env = dict(os.environ, QS_DUMP_DIR=out_dir, QS_DUMP_PARTICLE_CYCLES=str(particle_cycles), OMP_NUM_THREADS=str(threads))
-    subprocess.run([REF_DUMP] + [str(a) for a in argv], check=True, env=env, stdout=subprocess.DEVNULL)
+    subprocess.run([exe or REF_DUMP] + [str(a) for a in argv], check=True, env=env, stdout=subprocess.DEVNULL)
 
 
 # ---- oracle binding -----------------------------------------------------------------------------------

@@ -384,3 +384,40 @@ def test_strict_math_chain_reproduces_the_reference_binarys_tables(name, over, f
         assert ints == golden[c][0], "%s cycle %d" % (name, c)
         assert abs(flux - golden[c][1]) <= 1e-6 * abs(golden[c][1])
     mc.close()
+
+
+@pytest.mark.skipif(not os.path.exists(H.REF_DUMP_STRICT), reason="oracle/_ref/qs_dump_strict not built (make -C oracle ref; needs /root/reference)")
+@pytest.mark.parametrize("deck_name,over,cycles", [
+    ("CTS2_1", dict(nx=8, ny=8, nz=8, lx=8, ly=8, lz=8, nParticles=5120), 4),
+    ("Coral2_P1_1", dict(nx=8, ny=8, nz=8, lx=8, ly=8, lz=8, nParticles=20480), 4),
+    ("Coral2_P2_1", dict(nx=6, ny=6, nz=6, lx=6 / 11.0, ly=6 / 11.0, lz=6 / 11.0, nParticles=8640), 3),
+    ("NonFlatXC", dict(nx=5, ny=5, nz=5, lx=50, ly=50, lz=50, nParticles=3000, dt=5e-10), 3),
+    ("Homogeneous_v5", dict(nx=6, ny=6, nz=6, nParticles=4320), 3),
+])
+def test_strict_chain_equals_the_reference_in_strict_math_mode_record_for_record(tmp_path, deck_name, over, cycles):
+    """The checker of the GPU validation build is the strict-math chain (host cycleInit in strict mode + qso_track(strict=1)).
+    oracle/_ref/qs_dump_strict is the UNMODIFIED reference with log / sin / cos of its four tracking translation units mapped
+    to the same portable functions (oracle/strict_math_map.h): cycle after cycle its processing vault, its census vault --
+    every record, every byte -- and its balance row must equal the chain's.  With test_gpu_parity / test_gpu_literal (GPU ==
+    chain) this ties the device to the reference itself, not only to its printed tables."""
+    deck = decks.write_deck(decks.derive(deck_name, dict(over, nSteps=cycles)), str(tmp_path / "deck.inp"))
+    H.run_reference_dump(["-i", deck], str(tmp_path / "dump"), particle_cycles=cycles, threads=1, exe=H.REF_DUMP_STRICT)
+    mc = host.MonteCarlo(["-i", deck])
+    mc.set_strict_math(True)
+    dt = mc.get_double("dt")
+    n_census = 0
+    for c in range(cycles):
+        ref = H.read_qsd(str(tmp_path / "dump" / ("cycle_%03d.qsd" % c)))
+        mc.cycle_init()
+        vault = mc.processing()
+        want_in = H.particles_from_bytes(ref["tracking_input"])
+        assert H.sort_particles(vault).tobytes() == H.sort_particles(want_in).tobytes(), "cycle %d processing vault" % c
+        r = H.oracle_track(mc.image, dt, vault, strict=True, threads=1)
+        want_census = H.particles_from_bytes(ref["census"])
+        assert H.sort_particles(r.census).tobytes() == H.sort_particles(want_census).tobytes(), "cycle %d census records" % c
+        n_census += len(want_census)
+        mc.set_tracking_result(r.census, r.balance, r.flux.sum())
+        row, _ = mc.cycle_finalize()
+        assert np.array_equal(row, ref["balance"]), "cycle %d balance row" % c
+    assert n_census > 0
+    mc.close()
