@@ -375,15 +375,19 @@ def main():
             except Exception as e:
                 return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
-        # the bit-exact build on the headline workload: the price of --fmad=false + IEEE div/sqrt + the exact facet predicate
-        extras["validation_fom"] = resident(args.workload, True, 1, 3)
-        extras["workloads"] = {}
-        for name in SECONDARY:
-            if name != args.workload:
-                extras["workloads"][name] = resident(name, not args.fast, 2, 5)
-        # NonFlatXC again with the hot block left to the ordinary L2 policy: what the persisting window buys (north_star:
-        # "pinned in Blackwell's ~126 MB L2 via an access-policy window")
-        extras["workloads"]["NonFlatXC_no_l2_window"] = resident("NonFlatXC", not args.fast, 2, 5, env={"QSB_NO_L2_WINDOW": "1"})
+        # One GPU: the bit-exact build on the headline workload (the price of --fmad=false + IEEE div/sqrt + the exact facet
+        # predicate) and every other north_star workload.  Several GPUs: the parity check of the N-GPU run; the secondary
+        # workloads only on request (QSB_BENCH_EXTRAS_MULTI=1: seven more simulations of N ranks each take minutes, and the
+        # scaling ladder is about the headline)
+        if world == 1 or os.environ.get("QSB_BENCH_EXTRAS_MULTI"):
+            extras["validation_fom"] = resident(args.workload, True, 1, 3)
+            extras["workloads"] = {}
+            for name in SECONDARY:
+                if name != args.workload:
+                    extras["workloads"][name] = resident(name, not args.fast, 2, 5)
+            # NonFlatXC again with the hot block left to the ordinary L2 policy: what the persisting window buys (north_star:
+            # "pinned in Blackwell's ~126 MB L2 via an access-policy window")
+            extras["workloads"]["NonFlatXC_no_l2_window"] = resident("NonFlatXC", not args.fast, 2, 5, env={"QSB_NO_L2_WINDOW": "1"})
         if world > 1:
             extras["parity_check"] = parity_block(rank, world, local_rank, dist, grid)
     if world > 1:

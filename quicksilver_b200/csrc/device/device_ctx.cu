@@ -1061,8 +1061,11 @@ int qsb_track(qsb_ctx* c, qsb_track_stats* stats)
 #if QSB_OPT_BOUNDARY_FIRST
             // boundary first: list the slots of the cycle's initial population whose history may reach another GPU (first launch of
             // a cycle over a host-put / device-made population; not when the input is streamed or a launch continues a cycle)
-            if (c->event_mode && c->im.cell_near && c->consumed == 0 && c->n_in_aos == 0 && c->ready_prefix > 0 &&
-                c->ready_prefix < (1ull << 32) && std::getenv("QSB_NO_BOUNDARY_FIRST") == nullptr)
+            // OPT-IN (QSB_BOUNDARY_FIRST=1): parity-green and 3 % faster on 2 GPUs (profiles/r02_multi_gpu_lines.txt, call 24), but the
+            // round's GPU budget ended before it could be run on 4 and 8
+            static const bool boundary_first = [] { const char* e = std::getenv("QSB_BOUNDARY_FIRST"); return e && std::atoi(e) != 0; }();
+            if (boundary_first && c->event_mode && c->im.cell_near && c->consumed == 0 && c->n_in_aos == 0 && c->ready_prefix > 0 &&
+                c->ready_prefix < (1ull << 32))
             {
                 if (c->ready_prefix > c->prio_list_cap)
                 {

@@ -84,11 +84,13 @@ def test_n_gpu_run_equals_single_rank_oracle(tmp_path, deck_name, grid, n, per_c
         assert H.sort_particles(union).tobytes() == H.sort_particles(want_census[c]).tobytes(), "cycle %d census" % c
 
 
-@pytest.mark.parametrize("exchange,grid", [("peer", (2, 1, 1)), ("nccl", (2, 1, 1)), ("peer", (2, 2, 1))])
-def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange, grid):
+@pytest.mark.parametrize("exchange,grid,boundary_first", [("peer", (2, 1, 1), "0"), ("nccl", (2, 1, 1), "0"), ("peer", (2, 2, 1), "0"),
+                                                         ("peer", (2, 1, 1), "1"), ("peer", (2, 2, 1), "1")])
+def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange, grid, boundary_first):
     """the population stays on the GPUs from cycle to cycle (cycleInit on every device, split factor from the allreduced
     global count); rows and census must equal the single-rank CPU chain -- host cycleInit in strict-math mode + oracle.
-    Grid (2, 2, 1) on 2 GPUs: two domains per GPU."""
+    Grid (2, 2, 1) on 2 GPUs: two domains per GPU.  boundary_first = "1": the opt-in boundary-first list (QSB_BOUNDARY_FIRST,
+    DESIGN.md section 6) -- the order in which histories are tracked must not change a bit of the result."""
     world, (gx, gy, gz), n, per_cell, cycles = 2, grid, 8, 10, 3
     if _gpu_count() < world:
         pytest.skip("needs %d GPUs" % world)
@@ -103,7 +105,8 @@ def test_n_gpu_resident_cycles_equal_single_rank_cpu_chain(tmp_path, exchange, g
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(H.ROOT, "tests", "_exchange_worker.py"), str(out), str(cycles)] + argvN
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900,
-                         env=dict(os.environ, QSB_TEST_BACKEND="device", QSB_EXCHANGE=exchange, QSB_PEER_WATCHDOG_S="20", QSB_TEST_RESIDENT="1"))
+                         env=dict(os.environ, QSB_TEST_BACKEND="device", QSB_EXCHANGE=exchange, QSB_PEER_WATCHDOG_S="20", QSB_TEST_RESIDENT="1",
+                                  QSB_BOUNDARY_FIRST=boundary_first))
     assert res.returncode == 0, res.stdout[-3000:]
     ranks = [json.load(open(out / ("rank%d.json" % r))) for r in range(world)]
     assert sum(i["sent"] for r in ranks for i in r["info"]) > 0
