@@ -8,7 +8,12 @@
  * integer bit operations (classic Cody-Waite reduction + minimax polynomials), so the
  * SAME source compiled by gcc (-ffp-contract=off) and by nvcc (--fmad=false) produces
  * the same bits on the host and on sm_100a.  Accuracy is ~1 ulp, which is all the
- * physics needs; the fast build uses the CUDA math library instead.
+ * physics needs.  The FAST build uses the same functions, contracted to FMAs by nvcc
+ * (track_physics.cuh: m_log / m_sincos): the CUDA math library's out-of-line argument
+ * reduction is never needed for the arguments the tracking loop passes.
+ * Algorithms and coefficients: the classic public-domain fdlibm lineage (Sun Microsystems'
+ * e_log.c, k_sin.c, k_cos.c: Cody-Waite reduction by ln2 / pi/2 in two pieces, minimax
+ * polynomials L1..L7, S1..S6, C1..C6), restated for a restricted argument range.
  */
 #ifndef QS_STRICT_MATH_H
 #define QS_STRICT_MATH_H
