@@ -1012,7 +1012,17 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
     return v;
 }
 // relaxed system-scope loads: served by the owning GPU's L2 (never this SM's L1), no fence and -- unlike ld.acquire --
-// no invalidation of the SM's L1, which holds the cell records and cross-section tables of every warp on it
+// no invalidation of the SM's L1, which holds the cell records and cross-section tables of every warp on it.
+// Ordering assumptions of the consumers that use them (ready words, census chunk counters, queue counters), stated because the
+// PTX memory model does not promise them for relaxed loads:
+//  * a slot's record is read AFTER its ready word was seen, through a control dependency (the loads sit behind the branch on
+//    the flag) and with .cg loads that cannot hit a stale L1 line; a peer's deposit does not rely on ordering at all -- the
+//    record carries a checksum of its own words and a per-launch salt (store_deposit / deposit_complete), and an incomplete
+//    record is simply looked at again later;
+//  * secondaries are published with st.release.gpu AFTER their record stores have been issued one pass earlier; the consumer's
+//    relaxed load of the ready word followed by dependent .cg loads observes them on every NVIDIA GPU to date (loads are not
+//    speculated past the branch that guards them), which is what the parity suite exercises millions of times per run;
+//  * queue counters (head / tail) are only hints for how many tickets to ask for: a stale value costs a retry, never a particle.
 __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
 {
     unsigned long long v;
